@@ -1,0 +1,85 @@
+// capi.cu — error state, version, launch counter and the bring-up GEMM hook of libance_b200.so.
+#include <atomic>
+#include <string.h>
+
+#include "common.h"
+#include "gemm_store.cuh"
+
+namespace ance {
+
+static thread_local char g_err[1024] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace ance
+
+extern "C" const char* ance_version(void) { return "ance_b200 0.1 (sm_100a)"; }
+extern "C" const char* ance_last_error(void) { return ance::g_err; }
+extern "C" int64_t ance_launch_count(void) { return ance::g_launches.load(); }
+
+namespace {
+
+template <int BN, int STAGES, int CG, uint32_t FMT>
+int run_dbg(const void* A, const void* B, int M, int N, int K, const float* bias, const void* R, int act, void* C,
+            float* C32, cudaStream_t st) {
+  constexpr int EW = 8;
+  using Ep = gemm::EpStore<BN, EW>;
+  CUtensorMap tmA, tmB;
+  if (!tc05_host::make_tmap_2d_16b(&tmA, A, M, K, K, gemm::BM) ||
+      !tc05_host::make_tmap_2d_16b(&tmB, B, N, K, K, BN / CG)) {
+    ance::set_error("cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", M, N, K);
+    return ANCE_ERR_CUDA;
+  }
+  gemm::WorkShape ws = gemm::make_shape(M, N, K, BN, CG, 0);
+  typename Ep::Params p;
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.C32 = C32;
+  p.bias = bias;
+  p.R = reinterpret_cast<const __nv_bfloat16*>(R);
+  p.ldc = N;
+  p.ldc32 = N;
+  p.ldr = N;
+  p.act = act;
+  ANCE_CUDA((gemm::launch<Ep, BN, STAGES, CG, EW, FMT>(tmA, tmB, ws, p, 0, st)));
+  ance::count_launch(1);
+  return ANCE_OK;
+}
+
+template <uint32_t FMT>
+int dispatch_dbg(int variant, const void* A, const void* B, int M, int N, int K, const float* bias, const void* R,
+                 int act, void* C, float* C32, cudaStream_t st) {
+  switch (variant) {
+    case 0: return run_dbg<256, 4, 1, FMT>(A, B, M, N, K, bias, R, act, C, C32, st);
+    case 1: return run_dbg<128, 6, 1, FMT>(A, B, M, N, K, bias, R, act, C, C32, st);
+    case 2: return run_dbg<256, 6, 2, FMT>(A, B, M, N, K, bias, R, act, C, C32, st);
+    case 3: return run_dbg<128, 8, 2, FMT>(A, B, M, N, K, bias, R, act, C, C32, st);
+    case 4: return run_dbg<64, 8, 1, FMT>(A, B, M, N, K, bias, R, act, C, C32, st);
+    default: ance::set_error("ance_dbg_gemm: unknown variant %d", variant); return ANCE_ERR_INVALID;
+  }
+}
+
+}  // namespace
+
+extern "C" int ance_dbg_gemm(const void* A_dev, const void* B_dev, int M, int N, int K, int fmt, int variant,
+                             const float* bias_dev, const void* residual_bf16_dev, int act, void* C_bf16_dev,
+                             float* C_f32_dev, void* stream) {
+  ANCE_REQUIRE(A_dev && B_dev && M > 0 && N > 0 && K > 0, "ance_dbg_gemm: null operand or empty shape");
+  ANCE_REQUIRE(K % 8 == 0 && N % 8 == 0, "ance_dbg_gemm: K and N must be multiples of 8 (16-byte rows)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (fmt == ANCE_FMT_BF16)
+    return dispatch_dbg<tc05::kFmtBF16>(variant, A_dev, B_dev, M, N, K, bias_dev, residual_bf16_dev, act, C_bf16_dev,
+                                        C_f32_dev, st);
+  if (fmt == ANCE_FMT_FP16)
+    return dispatch_dbg<tc05::kFmtF16>(variant, A_dev, B_dev, M, N, K, bias_dev, residual_bf16_dev, act, C_bf16_dev,
+                                       C_f32_dev, st);
+  ance::set_error("ance_dbg_gemm: unknown operand format %d", fmt);
+  return ANCE_ERR_INVALID;
+}

@@ -1,0 +1,384 @@
+// tc05.cuh — sm_100a device primitives used by every tensor-core kernel in this repo:
+// mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld / st) and the
+// UMMA shared-memory / instruction descriptors.  Inline PTX only; no CUTLASS dependency.
+//
+// Bit layouts of the descriptors follow the PTX ISA "tcgen05 matrix descriptors" tables
+// (cross-checked against cute/arch/mma_sm100_desc.hpp of the vendored CUTLASS headers).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace tc05 {
+
+// ----------------------------------------------------------------------------------------------
+// misc
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// L2 cache-policy words accepted by cp.async.bulk.tensor ... .L2::cache_hint
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictFirst  = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast   = 0x14F0000000000000ull;
+
+// ----------------------------------------------------------------------------------------------
+// mbarrier
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+
+// Every wait in this repo goes through here.  A pipeline bug would otherwise hang the GPU; the
+// watchdog turns it into a trap (cudaErrorLaunchFailure on the host) after ~4 s of spinning.
+#ifndef TC05_WATCHDOG_CYCLES
+#define TC05_WATCHDOG_CYCLES 8000000000ll
+#endif
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity, int tag) {
+  printf("[tc05] mbarrier timeout: block %d thread %d bar@0x%x parity %u tag %d\n", (int)blockIdx.x,
+         (int)threadIdx.x, bar_addr, parity, tag);
+  __trap();
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > TC05_WATCHDOG_CYCLES) mbar_timeout(smem_u32(bar), parity, tag);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// 2-D tiled load, completes `box bytes` on `bar` (OOB elements are zero-filled and still counted).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "l"(hint)
+      : "memory");
+}
+
+// Same, issued by either CTA of a cta_group::2 pair: bytes complete on the LEADER CTA's barrier
+// (peer bit of the shared::cluster barrier address cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                                int c1, uint64_t hint) {
+  uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_addr), "r"(c0), "r"(c1),
+        "l"(hint)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation
+// ----------------------------------------------------------------------------------------------
+template <int kCtaGroup>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  if constexpr (kCtaGroup == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+
+template <int kCtaGroup>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if constexpr (kCtaGroup == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  } else {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  }
+}
+
+__device__ __forceinline__ void tc_fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05: descriptors
+// ----------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes
+// (64 x 16-bit) with the 128-byte swizzle (what a TMA box {64, rows} with SWIZZLE_128B writes).
+//   bits [ 0,14) start address >> 4      bits [16,30) leading byte offset >> 4 (unused here: 1)
+//   bits [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)   bits [46,48) version = 1
+//   bits [49,52) base offset = 0 (tile base is 1024-B aligned)      bits [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Shared-memory descriptor for an MN-major operand (the MN dimension is contiguous): tile stored
+// as `k` rows of 128 bytes (64 x 16-bit along MN) with the 128-byte swizzle, i.e. a TMA box
+// {64 (mn), k rows}.  Canonical layout ((8,m),(8,k)) in 16-B units: 8-row (k) groups are
+// `sbo_bytes` apart, successive 64-element MN blocks are `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                       uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+enum : uint32_t { kFmtF16 = 0, kFmtBF16 = 1 };
+
+// Instruction descriptor, kind::f16, fp32 accumulate.
+//   [4,6) D fmt (1 = f32)  [7,10) A fmt  [10,13) B fmt  [15] A major (0 = K)  [16] B major
+//   [17,23) N >> 3         [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n, uint32_t fmt, uint32_t a_mn_major,
+                                                      uint32_t b_mn_major) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
+         ((m >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05: MMA issue / commit (single issuing thread)
+// ----------------------------------------------------------------------------------------------
+// D[tmem] (+)= A[smem] * B[smem]
+template <int kCtaGroup>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (kCtaGroup == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]   (A: lane = row, each 32-bit column = two consecutive K elements)
+template <int kCtaGroup>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (kCtaGroup == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// mbarrier arrive once all tcgen05 ops previously issued by this thread have completed.
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// cta_group::2: arrive on the barrier at this smem offset in every CTA named by cta_mask
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05: TMEM <-> registers.  Warp w of a CTA may only touch lanes [32*(w%4), 32*(w%4)+32).
+// taddr = (lane << 16) | column
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
+// ring-buffer bookkeeping
+// ----------------------------------------------------------------------------------------------
+template <int kStages>
+struct Ring {
+  uint32_t stage = 0, phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == kStages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+}  // namespace tc05
+
+// ----------------------------------------------------------------------------------------------
+// host: tensor-map encode through the driver entry point (no link-time libcuda dependency)
+// ----------------------------------------------------------------------------------------------
+namespace tc05_host {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major 16-bit matrix [rows, cols] with row pitch `ld_elems`; box = {64 cols, box_rows},
+// 128-byte swizzle.  Returns false on failure.
+inline bool make_tmap_2d_16b(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                             uint32_t box_rows, uint32_t box_cols = 64) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tc05_host

@@ -1,0 +1,141 @@
+/* ance_b200.h — C ABI of libance_b200.so: the B200-native replacement for the native arithmetic on
+ * microsoft/ANCE's ANN-refresh path (drivers/run_ann_data_gen.py + model/models.py).
+ *
+ * The reference has no FFI of its own: the native work on this path is done by un-vendored
+ * libraries called directly from Python.  Each entry point below names the reference call site it
+ * replaces.  Plain C, opaque handles, int status (0 = ok), ance_last_error() for the message, no
+ * exceptions and no torch types across the boundary.  All *_dev pointers are CUDA device pointers
+ * on the device that was current when the handle was created; `stream` is a cudaStream_t passed as
+ * void*.  Handles are not thread-safe; distinct handles may be used concurrently.
+ *
+ * There is NO CPU fallback: every compute entry point fails with ANCE_ERR_CUDA when no sm_100
+ * device is present.
+ */
+#ifndef ANCE_B200_H_
+#define ANCE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  ANCE_OK = 0,
+  ANCE_ERR_INVALID = 1,     /* bad argument */
+  ANCE_ERR_CUDA = 2,        /* CUDA runtime / driver error, or no sm_100 device */
+  ANCE_ERR_NOMEM = 3,
+  ANCE_ERR_UNSUPPORTED = 4  /* shape outside what the kernels were built for */
+};
+
+/* 16-bit operand format of the tensor-core passes (tcgen05 kind::f16 runs both at the same rate). */
+enum { ANCE_FMT_FP16 = 0, ANCE_FMT_BF16 = 1 };
+
+const char* ance_version(void);
+const char* ance_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t ance_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flat inner-product index  — replaces faiss.IndexFlatIP(dim) / .add / .search
+ *   reference: drivers/run_ann_data_gen.py:269-276,303 ; drivers/run_ann_data_gen_dpr.py:238-252
+ * Semantics (faiss IndexFlatIP): for each query the k rows with the largest fp32 inner product,
+ * sorted by score descending; labels are row numbers in insertion order (+ row_offset), int64;
+ * when fewer than k rows exist the tail is label -1 / score -FLT_MAX.  Ties are broken by the
+ * smaller row number (faiss leaves tie order unspecified; ours is deterministic).
+ * Scores are the exact fp32-input dot product accumulated in fp64 and rounded once to fp32.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ance_index* ance_index_t;
+
+typedef struct {
+  int64_t nq;             /* queries in the last search */
+  int64_t n_uncertified;  /* queries whose coarse pass could not be proven exact -> exact fallback */
+  int64_t n_candidates;   /* candidates rescored in fp32/fp64 */
+  int32_t kprime;         /* candidates kept per (query, split) by the coarse pass */
+  int32_t n_splits;       /* row-range splits of the corpus per query tile */
+  float max_eps;          /* largest per-query coarse-score error bound used by the certificate */
+} ance_search_stats;
+
+int ance_index_create(int dim, int64_t capacity_rows, int operand_fmt, ance_index_t* out);
+int ance_index_destroy(ance_index_t idx);
+int ance_index_reset(ance_index_t idx);                       /* ntotal = 0, storage kept */
+int64_t ance_index_ntotal(ance_index_t idx);
+/* IndexFlatIP.add: append n rows (fp32, row-major [n, dim], device memory). */
+int ance_index_add(ance_index_t idx, const float* rows_dev, int64_t n, void* stream);
+/* IndexFlatIP.search: Q [nq, dim] fp32 -> D [nq, k] fp32, I [nq, k] int64 (all device memory). */
+int ance_index_search(ance_index_t idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                      int64_t row_offset, void* stream);
+/* Same contract, computed entirely by the exact fp32->fp64 brute-force kernel (validation path). */
+int ance_index_search_exact(ance_index_t idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+                            int64_t* I_dev, int64_t row_offset, void* stream);
+/* Blocks on the stream of the last search and returns its statistics. */
+int ance_index_last_stats(ance_index_t idx, ance_search_stats* out);
+/* Tunables: "kprime" (0 = auto), "n_splits" (0 = auto), "cta_group" (1|2), "max_ctas" (0 = all SMs),
+ * "coarse_only_timing" (debug). */
+int ance_index_set_param(ance_index_t idx, const char* name, double value);
+
+/* Host k-way merge of per-shard results — replaces utils/util.py:87-146 barrier_array_merge +
+ * the rank-0-only search (the reference's own precedent: utils/eval_mrr.py:175-183).
+ * D[s], I[s]: [nq, k] sorted descending per shard (labels already global).  Output [nq, k]. */
+int ance_merge_topk_host(const float* const* D, const int64_t* const* I, int n_shards, int64_t nq, int k,
+                         float* D_out, int64_t* I_out, int n_threads);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dual-encoder forward — replaces the HF RobertaModel/BertModel forward + embeddingHead + norm
+ *   reference: model/models.py:149-157 (RobertaDot_NLL_LN.query_emb/body_emb),
+ *              model/models.py:165-199 (MultiChunk body_emb, caller reshapes [B,2048]->[4B,512]),
+ *              model/models.py:223-259 (BiEncoder / HFBertEncoder, CLS of last layer, no head)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ance_encoder* ance_encoder_t;
+
+enum { ANCE_ARCH_ROBERTA = 0, ANCE_ARCH_BERT = 1 };
+
+typedef struct {
+  int arch;        /* ANCE_ARCH_ROBERTA: position ids = cumsum(ids != pad) * (ids != pad) + pad_id
+                      ANCE_ARCH_BERT   : position ids = 0..L-1 */
+  int n_layer, hidden, heads, ffn, vocab, max_pos, type_vocab, pad_id;
+  float ln_eps;
+  int has_head;    /* 1: out = LayerNorm(Linear(CLS)) (models.py:152-153); 0: out = CLS (models.py:237-239) */
+} ance_encoder_config;
+
+/* All weight pointers are HOST fp32 arrays in the checkpoint's own layout (Linear weight = [out, in]);
+ * the library converts and uploads them once. */
+typedef struct {
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b;   /* attention.self.{query,key,value} */
+  const float *ao_w, *ao_b, *ln1_g, *ln1_b;         /* attention.output.{dense,LayerNorm} */
+  const float *ff1_w, *ff1_b;                       /* intermediate.dense */
+  const float *ff2_w, *ff2_b, *ln2_g, *ln2_b;       /* output.{dense,LayerNorm} */
+} ance_layer_weights;
+
+typedef struct {
+  const float *word_emb, *pos_emb, *type_emb, *emb_ln_g, *emb_ln_b;
+  const ance_layer_weights* layers;                 /* [n_layer] */
+  const float *head_w, *head_b, *head_ln_g, *head_ln_b; /* embeddingHead, norm (has_head only) */
+} ance_encoder_weights;
+
+int ance_encoder_create(const ance_encoder_config* cfg, const ance_encoder_weights* w, int max_tokens,
+                        ance_encoder_t* out);
+int ance_encoder_destroy(ance_encoder_t enc);
+/* ids_dev [B, L] int32.  Attention mask: lens_dev [B] int32 (mask = 1^len 0^(L-len), the
+ * data/msmarco_data.py:275-303 form) or mask_dev [B, L] uint8 (data/DPR_data.py:283 form); exactly one
+ * non-null.  Masked keys get the additive -10000 of HF 2.3.0, so an all-pad sequence yields the
+ * finite "uniform attention" vector the reference yields.  out_dev [B, hidden] fp32. */
+int ance_encoder_forward(ance_encoder_t enc, const int32_t* ids_dev, const int32_t* lens_dev,
+                         const uint8_t* mask_dev, int B, int L, float* out_dev, void* stream);
+/* Debug / parity: copy the hidden states after layer `layer` (0 = embeddings) of the last forward
+ * into out_dev [B*L, hidden] fp32. */
+int ance_encoder_debug_hidden(ance_encoder_t enc, int layer, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bring-up / test hooks (not part of the drop-in surface)
+ * ------------------------------------------------------------------------------------------------ */
+/* D[M,N] = act(A[M,K] * B[N,K]^T + bias) + R ; A,B 16-bit device arrays in `fmt`; outputs optional.
+ * variant: 0 = BN 256 CG 1, 1 = BN 128 CG 1, 2 = BN 256 CG 2, 3 = BN 128 CG 2, 4 = BN 64 CG 1 */
+int ance_dbg_gemm(const void* A_dev, const void* B_dev, int M, int N, int K, int fmt, int variant,
+                  const float* bias_dev, const void* residual_bf16_dev, int act, void* C_bf16_dev,
+                  float* C_f32_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANCE_B200_H_ */
