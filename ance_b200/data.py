@@ -1,0 +1,191 @@
+"""Token-cache I/O of the ANN refresh: the reference's dataset surface plus a bulk reader.
+
+Drop-in for the reference's
+  * ``EmbeddingCache``     utils/util.py:257-307  (fixed-record binary token store)
+  * ``StreamingDataset``   utils/util.py:310-329  (rank-strided IterableDataset)
+  * ``GetProcessingFn``    data/msmarco_data.py:275-303 and data/DPR_data.py:276-296
+with the same names, argument meaning and error behaviour, so the trainer (which random-accesses
+the same caches, data/msmarco_data.py:348-358) and any code written against the reference keep
+working.  ``StridedBatchReader`` is what the B200 refresher itself uses: it memory-maps the file
+once, takes this rank's ``i % world_size == rank`` records with numpy (no per-record Python), and
+yields pinned ``(ids int32[B,L], lens int32[B], idx int64[B])`` batches; the attention mask is
+built on the GPU from ``lens`` (or from ``ids != 0`` for DPR).
+
+Record layout: 4-byte BIG-endian length, then L native int32 token ids.
+"""
+from __future__ import annotations
+
+import json
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch.utils.data import IterableDataset, TensorDataset
+
+
+class EmbeddingCache:
+    """Same contract as the reference class (utils/util.py:257-307)."""
+
+    def __init__(self, base_path, seed=-1):
+        self.base_path = base_path
+        with open(base_path + "_meta", "r") as f:
+            meta = json.load(f)
+            self.dtype = np.dtype(meta["type"])
+            self.total_number = meta["total_number"]
+            self.record_size = int(meta["embedding_size"]) * self.dtype.itemsize + 4
+        if seed >= 0:
+            self.ix_array = np.random.RandomState(seed).permutation(self.total_number)
+        else:
+            self.ix_array = np.arange(self.total_number)
+        self.f = None
+
+    # -- reference surface --------------------------------------------------------------------
+    def open(self):
+        self.f = open(self.base_path, "rb")
+
+    def close(self):
+        self.f.close()
+
+    def read_single_record(self):
+        record_bytes = self.f.read(self.record_size)
+        passage_len = int.from_bytes(record_bytes[:4], "big")
+        passage = np.frombuffer(record_bytes[4:], dtype=self.dtype)
+        return passage_len, passage
+
+    def __enter__(self):
+        self.open()
+        return self
+
+    def __exit__(self, type, value, traceback):
+        self.close()
+
+    def __getitem__(self, key):
+        # the reference's bound check is `key > total_number` (util.py:293, off by one); reading
+        # record `total_number` then fails later with an empty buffer.  Here it raises directly.
+        if key < 0 or key >= self.total_number:
+            raise IndexError(
+                "Index {} is out of bound for cached embeddings of size {}".format(key, self.total_number))
+        self.f.seek(key * self.record_size)
+        return self.read_single_record()
+
+    def __iter__(self):
+        self.f.seek(0)
+        for i in range(self.total_number):
+            new_ix = self.ix_array[i]
+            yield self.__getitem__(new_ix)
+
+    def __len__(self):
+        return self.total_number
+
+    # -- bulk access ----------------------------------------------------------------------------
+    @property
+    def embedding_size(self) -> int:
+        return (self.record_size - 4) // self.dtype.itemsize
+
+    def memmap(self) -> np.memmap:
+        """The whole file as a structured array: field 'len' (>i4) and 'ids' (int32[L])."""
+        rec = np.dtype([("len", ">i4"), ("ids", self.dtype, (self.embedding_size,))])
+        if self.total_number == 0:
+            return np.zeros((0,), dtype=rec)
+        return np.memmap(self.base_path, dtype=rec, mode="r", shape=(self.total_number,))
+
+
+class StreamingDataset(IterableDataset):
+    """Same contract as the reference class (utils/util.py:310-329): element i goes to rank
+    i % world_size; ``fn(element, i)`` yields the records."""
+
+    def __init__(self, elements, fn, distributed=True):
+        super().__init__()
+        self.elements = elements
+        self.fn = fn
+        self.num_replicas = -1
+        self.distributed = distributed
+
+    def __iter__(self):
+        if dist.is_available() and dist.is_initialized():
+            self.num_replicas = dist.get_world_size()
+            self.rank = dist.get_rank()
+        for i, element in enumerate(self.elements):
+            if self.distributed and self.num_replicas != -1 and i % self.num_replicas != self.rank:
+                continue
+            records = self.fn(element, i)
+            for rec in records:
+                yield rec
+
+
+def GetProcessingFn(args, query=False):
+    """data/msmarco_data.py:275-303: record -> [(input_ids int32[L], attention_mask bool[L],
+    token_type_ids uint8[L], idx int64)]."""
+
+    def fn(vals, i):
+        passage_len, passage = vals
+        max_len = args.max_query_length if query else args.max_seq_length
+        pad_len = max(0, max_len - passage_len)
+        token_type_ids = ([0] if query else [1]) * passage_len + [0] * pad_len
+        attention_mask = [1] * passage_len + [0] * pad_len
+        dataset = TensorDataset(
+            torch.tensor(np.asarray(passage)[None, :], dtype=torch.int),
+            torch.tensor([attention_mask], dtype=torch.bool),
+            torch.tensor([token_type_ids], dtype=torch.uint8),
+            torch.tensor([i], dtype=torch.long))
+        return [ts for ts in dataset]
+
+    return fn
+
+
+def GetProcessingFnDPR(args, query=False):
+    """data/DPR_data.py:276-296: as above but attention_mask = ids != 0 and token types all 0."""
+
+    def fn(vals, i):
+        passage_len, passage = vals
+        passage = np.asarray(passage)
+        dataset = TensorDataset(
+            torch.tensor(passage[None, :], dtype=torch.int),
+            torch.tensor((passage != 0)[None, :], dtype=torch.bool),
+            torch.zeros((1, passage.shape[0]), dtype=torch.uint8),
+            torch.tensor([i], dtype=torch.long))
+        return [ts for ts in dataset]
+
+    return fn
+
+
+class StridedBatchReader:
+    """Bulk, rank-strided batches of one token cache.
+
+    Yields ``(ids, lens, idx)`` with exactly the records, order and batch boundaries the
+    reference's ``DataLoader(StreamingDataset(cache, fn), batch_size=B)`` produces on this rank
+    (run_ann_data_gen.py:199-202): records ``rank, rank+W, rank+2W, ...`` in groups of B, last
+    batch ragged.  Tensors are pinned when CUDA is available so the H2D copy can be asynchronous.
+    """
+
+    def __init__(self, cache: EmbeddingCache, batch_size: int, rank: int = 0, world_size: int = 1,
+                 max_len: Optional[int] = None, pin: Optional[bool] = None):
+        if batch_size <= 0:
+            raise ValueError("batch_size must be positive")
+        self.cache = cache
+        self.batch_size = int(batch_size)
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.L = cache.embedding_size
+        if max_len is not None and max_len != self.L:
+            raise ValueError(f"cache records hold {self.L} tokens but max length {max_len} was requested")
+        self.pin = torch.cuda.is_available() if pin is None else pin
+        self.n_local = len(range(self.rank, cache.total_number, self.world_size))
+
+    def __len__(self) -> int:
+        return (self.n_local + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        mm = self.cache.memmap()
+        n, W, B = self.cache.total_number, self.world_size, self.batch_size
+        for b0 in range(0, self.n_local, B):
+            first = self.rank + b0 * W
+            stop = min(n, self.rank + (b0 + B) * W)
+            idx = np.arange(first, stop, W, dtype=np.int64)
+            recs = mm[first:stop:W]
+            ids = torch.from_numpy(np.ascontiguousarray(recs["ids"], dtype=np.int32))
+            lens = torch.from_numpy(np.ascontiguousarray(recs["len"]).astype(np.int32))
+            idx_t = torch.from_numpy(idx)
+            if self.pin:
+                ids, lens = ids.pin_memory(), lens.pin_memory()
+            yield ids, lens, idx_t

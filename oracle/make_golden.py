@@ -1,0 +1,300 @@
+"""Generate tests/golden/* by running the REFERENCE's own code (imported from /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+What is pinned:
+  encoder_*.npz   outputs of the reference classes model/models.py:137-199,223-259 (RobertaDot_NLL_LN,
+                  RobertaDot_CLF_ANN_NLL_MultiChunk, BiEncoder) on seeded random weights
+                  (oracle.encoder_oracle.random_roberta_state_dict — regenerated, not stored) and fixed
+                  token ids.  The installed transformers is 5.5.0, not the pinned 2.3.0: configs need
+                  return_dict=False (models.py:45 asserts a tuple), and 5.x masks with dtype-min instead
+                  of the additive -10000, which changes ONLY all-padding sequences (a constant vector
+                  either way).  Those rows are stored separately (`allpad_*`) and the oracle keeps the
+                  2.3.0 semantics the reference was written against.
+  refresh_*.json  the reference's own post-processing (GenerateNegativePassaageID, EvalDevQuery, the
+                  ann_training_data writer inside generate_new_ann, drivers/run_ann_data_gen.py:231-440)
+                  executed with the un-importable third-party pieces stubbed: faiss.IndexFlatIP by
+                  oracle.flat_ip_oracle, pytrec_eval by oracle.refresh_oracle.ndcg_cut, the model by
+                  seeded random embeddings.  Also utils/util.py EmbeddingCache / StreamingDataset /
+                  barrier merge order and data/msmarco_data.py GetProcessingFn on a tiny cache.
+"""
+import argparse
+import json
+import os
+import random
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import flat_ip_oracle, refresh_oracle  # noqa: E402
+from oracle.encoder_oracle import (BiEncoderOracle, RobertaDotOracle, random_roberta_state_dict)  # noqa: E402
+
+
+def stub_third_party():
+    sys.path.append(REF)
+    for m in ("pytrec_eval", "faiss", "tensorboardX"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules["tensorboardX"].SummaryWriter = object
+    import transformers
+    # drivers/run_ann_data_gen.py:18-25 imports AdamW (removed in transformers 5.x) and never uses it
+    transformers.__dict__.setdefault("AdamW", torch.optim.AdamW)
+
+
+def make_ids(rng, B, L, lens, pad, vocab, cls=0, sep=2):
+    ids = np.full((B, L), pad, dtype=np.int32)
+    for b in range(B):
+        n = int(lens[b])
+        if n > 0:
+            ids[b, :n] = rng.integers(3, vocab, size=n)
+            ids[b, 0] = cls
+            ids[b, n - 1] = sep
+    return ids
+
+
+def golden_encoders():
+    from transformers import BertConfig, RobertaConfig
+    import model.models as M
+
+    rng = np.random.default_rng(0)
+    # ---------------- rdot_nll ----------------
+    sd = random_roberta_state_dict(seed=0)
+    cfg = RobertaConfig(vocab_size=50265, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                        intermediate_size=3072, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5,
+                        pad_token_id=1, bos_token_id=0, eos_token_id=2, num_labels=2, return_dict=False,
+                        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    ref = M.RobertaDot_NLL_LN(cfg).eval()
+    missing, unexpected = ref.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith("classifier.") or "pooler" in k or "position_ids" in k for k in missing), missing
+    lens = np.array([128, 97, 64, 33, 17, 8, 128, 76], dtype=np.int32)
+    ids = make_ids(rng, 8, 128, lens, 1, 50265)
+    mask = (np.arange(128)[None, :] < lens[:, None])
+    with torch.no_grad():
+        emb = ref.body_emb(torch.from_numpy(ids).long(), torch.from_numpy(mask).long()).numpy()
+    orc = RobertaDotOracle(sd)
+    o = orc.body_emb(torch.from_numpy(ids), torch.from_numpy(mask)).numpy()
+    print("rdot_nll: oracle vs reference max abs diff", np.abs(o - emb).max())
+    assert np.abs(o - emb).max() < 2e-4
+    qlens = np.array([64, 9, 12, 5], dtype=np.int32)
+    qids = make_ids(rng, 4, 64, qlens, 1, 50265)
+    qmask = (np.arange(64)[None, :] < qlens[:, None])
+    with torch.no_grad():
+        qemb = ref.query_emb(torch.from_numpy(qids).long(), torch.from_numpy(qmask).long()).numpy()
+    assert np.abs(orc.query_emb(torch.from_numpy(qids), torch.from_numpy(qmask)).numpy() - qemb).max() < 2e-4
+    np.savez_compressed(os.path.join(GOLD, "encoder_rdot_nll.npz"), seed=0, ids=ids, lens=lens, emb=emb,
+                        qids=qids, qlens=qlens, qemb=qemb)
+
+    # ---------------- rdot_nll_multi_chunk ----------------
+    refm = M.RobertaDot_CLF_ANN_NLL_MultiChunk(cfg).eval()
+    refm.load_state_dict(sd, strict=False)
+    dlens = np.array([2048, 700], dtype=np.int32)  # doc 1: chunk 0 full, chunk 1 partial, chunks 2-3 all padding
+    dids = make_ids(rng, 2, 2048, dlens, 1, 50265)
+    dmask = (np.arange(2048)[None, :] < dlens[:, None])
+    with torch.no_grad():
+        demb = refm.body_emb(torch.from_numpy(dids).long(), torch.from_numpy(dmask).long()).numpy()
+    od = orc.body_emb_multi_chunk(torch.from_numpy(dids), torch.from_numpy(dmask)).numpy()
+    real = np.array([[1, 1, 1, 1], [1, 1, 0, 0]], dtype=bool)
+    print("multi_chunk: oracle vs reference, chunks with tokens:", np.abs(od - demb)[real].max(),
+          " all-pad chunks (transformers 5.x vs 2.3.0 mask semantics):", np.abs(od - demb)[~real].max())
+    assert np.abs(od - demb)[real].max() < 2e-4
+    assert np.abs(od[1, 2] - od[1, 3]).max() == 0.0 and np.abs(demb[1, 2] - demb[1, 3]).max() == 0.0
+    np.savez_compressed(os.path.join(GOLD, "encoder_multi_chunk.npz"), seed=0, ids=dids, lens=dlens, emb=demb,
+                        real_chunk=real, allpad_oracle_2_3_0=od[1, 2])
+
+    # ---------------- dpr ----------------
+    bcfg = BertConfig(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                      intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
+                      pad_token_id=0, return_dict=False, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sdq = random_roberta_state_dict(seed=1, vocab=30522, max_pos=512, head=False, prefix="question_model.")
+    sdc = random_roberta_state_dict(seed=2, vocab=30522, max_pos=512, head=False, prefix="ctx_model.")
+    sdd = {**sdq, **sdc}
+    be = M.BiEncoder.__new__(M.BiEncoder)  # the constructor downloads bert-base-uncased (models.py:228-233)
+    torch.nn.Module.__init__(be)
+    be.question_model = M.HFBertEncoder(bcfg)
+    be.ctx_model = M.HFBertEncoder(bcfg)
+    missing, unexpected = be.load_state_dict(sdd, strict=False)
+    assert not unexpected, unexpected
+    assert all("pooler" in k or "position_ids" in k for k in missing), missing
+    be.eval()
+    plens = np.array([256, 120, 31, 256], dtype=np.int32)
+    pids = make_ids(rng, 4, 256, plens, 0, 30522, cls=101, sep=102)
+    with torch.no_grad():
+        pemb = be.body_emb(torch.from_numpy(pids).long(), torch.from_numpy(pids != 0).long()).numpy()
+        qemb2 = be.query_emb(torch.from_numpy(pids).long(), torch.from_numpy(pids != 0).long()).numpy()
+    bo = BiEncoderOracle(sdd)
+    d1 = np.abs(bo.body_emb(torch.from_numpy(pids), torch.from_numpy(pids != 0)).numpy() - pemb).max()
+    d2 = np.abs(bo.query_emb(torch.from_numpy(pids), torch.from_numpy(pids != 0)).numpy() - qemb2).max()
+    print("dpr: oracle vs reference", d1, d2)
+    assert d1 < 2e-4 and d2 < 2e-4
+    np.savez_compressed(os.path.join(GOLD, "encoder_dpr.npz"), seed_q=1, seed_c=2, ids=pids, lens=plens,
+                        body_emb=pemb, query_emb=qemb2)
+
+
+def golden_io():
+    """utils/util.py + data/msmarco_data.py on a tiny cache."""
+    from utils.util import EmbeddingCache, StreamingDataset
+    from data.msmarco_data import GetProcessingFn
+
+    rng = np.random.default_rng(1)
+    N, L = 37, 16
+    lens = rng.integers(1, L + 1, size=N)
+    ids = make_ids(rng, N, L, lens, 1, 1000)
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        base = os.path.join(td, "passages")
+        refresh_oracle.write_cache(base, lens, ids)
+        raw = open(base, "rb").read()
+        out["file_sha_len"] = len(raw)
+        out["first_record_hex"] = raw[:4 + 4 * L].hex()
+        cache = EmbeddingCache(base)
+        with cache as c:
+            l5, p5 = c[5]
+            assert l5 == lens[5] and (p5 == ids[5]).all()
+            args = argparse.Namespace(max_seq_length=L, max_query_length=L)
+            fn = GetProcessingFn(args, query=False)
+            rec = fn((l5, p5), 5)[0]
+            out["proc_fn"] = {"ids": rec[0].tolist(), "mask": rec[1].int().tolist(), "type": rec[2].tolist(),
+                              "idx": int(rec[3]), "dtypes": [str(t.dtype) for t in rec]}
+            fnq = GetProcessingFn(args, query=True)
+            out["proc_fn_query_type"] = fnq((l5, p5), 5)[0][2].tolist()
+            # non-distributed streaming order
+            ds = StreamingDataset(c, fn)
+            out["stream_idx_w1"] = [int(r[3]) for r in ds]
+    out["N"], out["L"] = N, L
+    out["lens"] = lens.tolist()
+    out["ids"] = ids.tolist()
+    with open(os.path.join(GOLD, "refresh_io.json"), "w") as f:
+        json.dump(out, f)
+
+
+def golden_postprocess():
+    """Run the reference's generate_new_ann with the third-party pieces stubbed."""
+    sys.modules["transformers"].__dict__.setdefault("AdamW", torch.optim.AdamW)
+    import drivers.run_ann_data_gen as drv
+
+    rng = np.random.default_rng(2)
+    n_p, n_q, n_dev, dim, W, B = 2000, 120, 40, 32, 4, 16
+    P = rng.standard_normal((n_p, dim)).astype(np.float32)
+    Q = rng.standard_normal((n_q, dim)).astype(np.float32)
+    Qd = rng.standard_normal((n_dev, dim)).astype(np.float32)
+    p2id = np.array(refresh_oracle.merged_embedding2id(n_p, W, B), dtype=np.int64)
+    q2id = np.array(refresh_oracle.merged_embedding2id(n_q, W, B), dtype=np.int64)
+    d2id = np.array(refresh_oracle.merged_embedding2id(n_dev, W, B), dtype=np.int64)
+    # the passage rows follow the merged order: row r holds the embedding of record p2id[r]
+    Prow, Qrow, Drow = P[p2id], Q[q2id], Qd[d2id]
+    train_pos = {int(q): int(rng.integers(0, n_p)) for q in range(n_q)}
+    # plant the positive among the neighbours of some queries so the skip / MRR branches run
+    for q in range(0, n_q, 3):
+        Q[q] = P[train_pos[q]] * 3 + Q[q] * 0.1
+    Qrow = Q[q2id]
+    dev_pos = {}
+    for q in range(n_dev):
+        dev_pos[q] = {int(rng.integers(0, n_p)): 1}
+        if q % 2 == 0:
+            pid = next(iter(dev_pos[q]))
+            Qd[q] = P[pid] * 3 + Qd[q] * 0.1
+    Drow = Qd[d2id]
+
+    class FakeIndex:
+        def __init__(self, d):
+            self.x = None
+
+        def add(self, x):
+            self.x = x
+
+        def search(self, q, k):
+            return flat_ip_oracle.search_bruteforce(self.x, q, k)
+
+    drv.faiss.omp_set_num_threads = lambda n: None
+    drv.faiss.IndexFlatIP = FakeIndex
+
+    class FakeEvaluator:
+        def __init__(self, qrel, measures):
+            self.qrel = qrel
+
+        def evaluate(self, run):
+            res = {}
+            for qid, docs in run.items():
+                if qid not in self.qrel:
+                    continue
+                ranked = [int(d) for d, _ in sorted(docs.items(), key=lambda kv: -kv[1])]
+                res[qid] = {"ndcg_cut_10": refresh_oracle.ndcg_cut(
+                    ranked, {int(k): v for k, v in self.qrel[qid].items()}, 10)}
+            return res
+
+    drv.pytrec_eval.RelevanceEvaluator = FakeEvaluator
+    calls = iter([(Drow, d2id), (Prow, p2id), (Qrow, q2id)])
+    drv.StreamInferenceDoc = lambda *a, **k: next(calls)
+    drv.load_model = lambda args, ckpt: (None, None, None)
+    drv.is_first_worker = lambda: True
+    drv.GetProcessingFn = lambda *a, **k: None
+    golden = {"n_p": n_p, "n_q": n_q, "n_dev": n_dev, "dim": dim, "W": W, "B": B, "seed": 2}
+    with tempfile.TemporaryDirectory() as td:
+        data_dir = os.path.join(td, "data")
+        os.makedirs(data_dir)
+        for nm, n in (("dev-query", n_dev), ("passages", n_p), ("train-query", n_q)):
+            refresh_oracle.write_cache(os.path.join(data_dir, nm), np.ones(n, dtype=np.int32),
+                                       np.zeros((n, 4), dtype=np.int32))
+        out_dir = os.path.join(td, "out")
+        os.makedirs(out_dir)
+        for variant, topk_mrr, chunk_factor, output_num in (("shuffle", False, 1, 0), ("topk", True, 3, 4)):
+            calls = iter([(Drow, d2id), (Prow, p2id), (Qrow, q2id)])
+            drv.StreamInferenceDoc = lambda *a, **k: next(calls)
+            args = argparse.Namespace(data_dir=data_dir, output_dir=out_dir, topk_training=20, negative_sample=5,
+                                      ann_chunk_factor=chunk_factor, ann_measure_topk_mrr=topk_mrr, inference=False,
+                                      rank=0, max_seq_length=4, max_query_length=4)
+            random.seed(0)
+            ndcg, nq_dev = drv.generate_new_ann(args, output_num, "ckpt/checkpoint-7/", train_pos, dev_pos, 7)
+            golden[variant] = {
+                "output_num": output_num, "chunk_factor": chunk_factor, "topk_mrr": topk_mrr,
+                "ndcg": ndcg, "num_queries_dev": nq_dev,
+                "training_data": open(os.path.join(out_dir, f"ann_training_data_{output_num}")).read(),
+                "ndcg_file": open(os.path.join(out_dir, f"ann_ndcg_{output_num}")).read(),
+            }
+        # resume bookkeeping (utils/util.py:224-243)
+        from utils.util import get_checkpoint_no, get_latest_ann_data
+        golden["latest_ann"] = list(get_latest_ann_data(out_dir)[:1])
+        golden["checkpoint_no"] = {p: get_checkpoint_no(p) for p in
+                                   ("checkpoint-150000", "a/b12/checkpoint-7/", "nodigits", "x9/y")}
+    golden["train_pos"] = {str(k): v for k, v in train_pos.items()}
+    golden["dev_pos"] = {str(k): {str(a): b for a, b in v.items()} for k, v in dev_pos.items()}
+    with open(os.path.join(GOLD, "refresh_postprocess.json"), "w") as f:
+        json.dump(golden, f)
+    print("postprocess golden: ndcg", golden["shuffle"]["ndcg"], golden["topk"]["ndcg"],
+          "lines", golden["shuffle"]["training_data"].count("\n"), golden["topk"]["training_data"].count("\n"))
+
+
+def golden_search():
+    """No reference arithmetic exists to run here (faiss absent): the search KAT pins the ORACLE itself
+    (definition-level brute force) so later edits cannot drift, with planted duplicates and ties."""
+    rng = np.random.default_rng(3)
+    P = rng.standard_normal((3000, 64)).astype(np.float32)
+    P[1500:1510] = P[10:20]           # exact duplicate rows -> exact ties
+    Q = rng.standard_normal((16, 64)).astype(np.float32)
+    Q[0] = P[12] * 2                   # its top-1 is a tie between rows 12 and 1502
+    D, I = flat_ip_oracle.search_bruteforce(P, Q, 20)
+    D2, I2 = flat_ip_oracle.search(P, Q, 20, slack=32, q_block=8, p_block=700)
+    assert (I == I2).all() and (D == D2).all()
+    np.savez_compressed(os.path.join(GOLD, "search_kat.npz"), seed=3, D=D, I=I)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    stub_third_party()
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    golden_search()
+    golden_io()
+    golden_postprocess()
+    golden_encoders()
+    print("golden fixtures written to", GOLD)
