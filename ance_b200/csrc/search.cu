@@ -413,7 +413,8 @@ struct ExactParams {
   const float* P;
   int d;
   int64_t n_rows;
-  const int* qlist;      // query numbers (null = identity)
+  const int* qlist;      // query numbers (null = q_base + i)
+  int q_base;
   const int* nq_dev;     // number of queries on the device (null = use nq)
   int nq;
   int k;                 // <= 512
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(256) exact_chunk_kernel(const ExactParams p) {
       const int qi = i / p.d, e = i - qi * p.d;
       float v = 0.f;
       if (qi < nqb) {
-        const int q = p.qlist ? p.qlist[g * kExQB + qi] : g * kExQB + qi;
+        const int q = p.qlist ? p.qlist[g * kExQB + qi] : p.q_base + g * kExQB + qi;
         v = p.Q[static_cast<size_t>(q) * p.d + e];
       }
       qs[i] = v;
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(256) exact_merge_kernel(const ExactParams p, f
   __shared__ uint64_t keys[kMergeBuf];
   const int nq = p.nq_dev ? min(*p.nq_dev, p.nq) : p.nq;
   for (int qi = blockIdx.x; qi < nq; qi += gridDim.x) {
-    const int q = p.qlist ? p.qlist[qi] : qi;
+    const int q = p.qlist ? p.qlist[qi] : p.q_base + qi;
     const uint64_t* src = p.chunk_keys + static_cast<size_t>(qi) * p.n_chunks * p.k;
     const int total = p.n_chunks * p.k;
     int have = 0;  // keys[0..have) = current best (sorted)
@@ -643,23 +644,24 @@ int launch_coarse(ance_index* ix, int64_t nq, int kprime, int n_splits_req, int*
   return ANCE_OK;
 }
 
-int run_exact(ance_index* ix, const float* Q, const int* qlist, const int* nq_dev, int nq_cap, int k, float* D,
-              int64_t* I, int64_t row_offset, cudaStream_t st) {
+constexpr int kExactBatch = 1024;  // queries per brute-force pass (bounds the chunk_keys scratch)
+
+int run_exact(ance_index* ix, const float* Q, const int* qlist, int nq, int k, float* D, int64_t* I,
+              int64_t row_offset, cudaStream_t st) {
   ExactParams ep;
   ep.Q = Q;
   ep.P = ix->P32;
   ep.d = ix->dim;
   ep.n_rows = ix->n;
-  ep.qlist = qlist;
-  ep.nq_dev = nq_dev;
-  ep.nq = nq_cap;
-  ep.k = std::min<int64_t>(k, std::max<int64_t>(ix->n, 1));
+  ep.nq_dev = nullptr;
+  ep.k = static_cast<int>(std::min<int64_t>(k, std::max<int64_t>(ix->n, 1)));
   ep.k = std::min(ep.k, 512);
   const int sms = gemm::sm_count();
   int n_chunks = static_cast<int>(std::min<int64_t>(2 * sms, (ix->n + 4095) / 4096));
   if (n_chunks < 1) n_chunks = 1;
   ep.n_chunks = n_chunks;
-  int rc = ensure(&ix->chunk_keys, &ix->chunk_keys_elems, static_cast<size_t>(nq_cap) * n_chunks * ep.k);
+  const int batch = std::min(nq, kExactBatch);
+  int rc = ensure(&ix->chunk_keys, &ix->chunk_keys_elems, static_cast<size_t>(batch) * n_chunks * ep.k);
   if (rc) return rc;
   ep.chunk_keys = ix->chunk_keys;
   const size_t smem = static_cast<size_t>(kExQB) * kExBuf * 8 + static_cast<size_t>(kExQB) * ix->dim * 4;
@@ -668,12 +670,18 @@ int run_exact(ance_index* ix, const float* Q, const int* qlist, const int* nq_de
     ANCE_CUDA(cudaFuncSetAttribute(exact_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
-  const int gy = std::max(1, std::min((nq_cap + kExQB - 1) / kExQB, 128));
-  exact_chunk_kernel<<<dim3(n_chunks, gy), 256, smem, st>>>(ep);
-  ANCE_CUDA(cudaGetLastError());
-  exact_merge_kernel<<<std::max(1, std::min(nq_cap, 4 * sms)), 256, 0, st>>>(ep, D, I, k, row_offset);
-  ANCE_CUDA(cudaGetLastError());
-  ance::count_launch(2);
+  for (int b0 = 0; b0 < nq; b0 += kExactBatch) {
+    const int nb = std::min(kExactBatch, nq - b0);
+    ep.qlist = qlist ? qlist + b0 : nullptr;
+    ep.q_base = b0;
+    ep.nq = nb;
+    const int gy = std::max(1, std::min((nb + kExQB - 1) / kExQB, 128));
+    exact_chunk_kernel<<<dim3(n_chunks, gy), 256, smem, st>>>(ep);
+    ANCE_CUDA(cudaGetLastError());
+    exact_merge_kernel<<<std::max(1, std::min(nb, 4 * sms)), 256, 0, st>>>(ep, D, I, k, row_offset);
+    ANCE_CUDA(cudaGetLastError());
+    ance::count_launch(2);
+  }
   return ANCE_OK;
 }
 
@@ -779,7 +787,7 @@ extern "C" int ance_index_search_exact(ance_index_t ix, const float* q_dev, int6
     ANCE_CUDA(cudaStreamSynchronize(st));
     return ANCE_OK;
   }
-  return run_exact(ix, q_dev, nullptr, nullptr, static_cast<int>(nq), k, D_dev, I_dev, row_offset, st);
+  return run_exact(ix, q_dev, nullptr, static_cast<int>(nq), k, D_dev, I_dev, row_offset, st);
 }
 
 extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq, int k, float* D_dev,
@@ -876,13 +884,22 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
   rescore_kernel<<<static_cast<unsigned>(nq), 256, rs_smem, st>>>(rp);
   ANCE_CUDA(cudaGetLastError());
   ance::count_launch(1);
-  // --- 4. exact fallback for the uncertified queries (device-side count; no host sync)
-  rc = run_exact(ix, q_dev, ix->flagged, ix->counters, static_cast<int>(nq), k, D_dev, I_dev, row_offset, st);
-  if (rc) return rc;
+  // --- 4. exact fallback for the uncertified queries.  One small D2H + sync per search tells the host
+  // how many there are (the reference's search call is synchronous as well).
+  int h[4] = {0, 0, 0, 0};
+  ANCE_CUDA(cudaMemcpyAsync(h, ix->counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+  ANCE_CUDA(cudaStreamSynchronize(st));
+  if (h[0] > 0) {
+    rc = run_exact(ix, q_dev, ix->flagged, h[0], k, D_dev, I_dev, row_offset, st);
+    if (rc) return rc;
+  }
   ix->stats = ance_search_stats{};
   ix->stats.nq = nq;
   ix->stats.kprime = kprime;
   ix->stats.n_splits = ns;
+  ix->stats.n_uncertified = h[0];
+  ix->stats.n_candidates = h[1];
+  memcpy(&ix->stats.max_eps, &h[2], 4);
   ix->last_stream = st;
   ix->stats_pending = true;
   return ANCE_OK;
@@ -891,14 +908,9 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
 extern "C" int ance_index_last_stats(ance_index_t ix, ance_search_stats* out) {
   ANCE_REQUIRE(ix != nullptr && out != nullptr, "ance_index_last_stats: null argument");
   if (ix->stats_pending) {
-    int h[4] = {0, 0, 0, 0};
     int err = 0;
     ANCE_CUDA(cudaStreamSynchronize(ix->last_stream));
-    ANCE_CUDA(cudaMemcpy(h, ix->counters, sizeof(h), cudaMemcpyDeviceToHost));
     ANCE_CUDA(cudaMemcpy(&err, ix->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-    ix->stats.n_uncertified = h[0];
-    ix->stats.n_candidates = h[1];
-    memcpy(&ix->stats.max_eps, &h[2], 4);
     ix->stats_pending = false;
     if (err) {
       ance::set_error("non-finite value after rounding to the 16-bit operand format (use ANCE_FMT_BF16 for data outside the fp16 range)");

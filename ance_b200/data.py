@@ -183,8 +183,8 @@ class StridedBatchReader:
             stop = min(n, self.rank + (b0 + B) * W)
             idx = np.arange(first, stop, W, dtype=np.int64)
             recs = mm[first:stop:W]
-            ids = torch.from_numpy(np.ascontiguousarray(recs["ids"], dtype=np.int32))
-            lens = torch.from_numpy(np.ascontiguousarray(recs["len"]).astype(np.int32))
+            ids = torch.from_numpy(np.array(recs["ids"], dtype=np.int32, order="C"))
+            lens = torch.from_numpy(np.array(recs["len"]).astype(np.int32))
             idx_t = torch.from_numpy(idx)
             if self.pin:
                 ids, lens = ids.pin_memory(), lens.pin_memory()

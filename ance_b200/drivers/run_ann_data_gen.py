@@ -1,0 +1,412 @@
+"""B200-native ANN refresher — drop-in for the reference's drivers/run_ann_data_gen.py.
+
+Same CLI flags, same inputs (`training_dir/checkpoint-N/` with scheduler.pt, `data_dir/{passages,
+train-query,dev-query}` token caches + qrels) and same outputs (`output_dir/ann_training_data_N`,
+`ann_ndcg_N`, `--inference` dumps), so it runs under the unmodified trainer (drivers/run_ann.py
+picks the files up at run_ann.py:182-228).  What changes is where the work happens:
+
+  reference (run_ann_data_gen.py)                       here
+  ---------------------------------------------------   ------------------------------------------------
+  per-record Python dataloader, batch 16 (199-202)      StridedBatchReader: memmap + numpy stride, pinned
+  HF eager fp32 forward, D2H every batch (175-180)      libance_b200 encoder (tcgen05 GEMMs, fused attention);
+                                                        embeddings stay in this rank's HBM
+  np.save / np.load gather to rank 0 (util.py:87-146)   rows never move; ONE all-gather of query embeddings
+  faiss.IndexFlatIP on rank 0, 16 threads (269-303)     per-shard sm_100a flat-IP top-k + host k-way merge
+  Python loops for negatives / NDCG (339-440)           numpy (ance_b200/postprocess.py)
+
+Row numbering is the reference's: rank r encodes records r, r+W, ...; global row = (rows of ranks
+< r) + local row, i.e. the order barrier_array_merge produces (util.py:129-144); MaxP rows are
+chunk-major per `per_gpu_eval_batch_size` batch (run_ann_data_gen.py:183-186).
+"""
+from __future__ import annotations
+
+import argparse
+import csv
+import logging
+import os
+import random
+import time
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..data import EmbeddingCache, StridedBatchReader
+from ..models import MSMarcoConfigDict
+from .. import postprocess
+
+logger = logging.getLogger(__name__)
+
+
+# =============================================================================================
+# bookkeeping (same behaviour as the reference helpers)
+# =============================================================================================
+def get_checkpoint_no(checkpoint_path: str) -> int:
+    """utils/util.py:224-226."""
+    import re
+    nums = re.findall(r"\d+", checkpoint_path)
+    return int(nums[-1]) if len(nums) > 0 else 0
+
+
+def get_latest_ann_data(ann_data_path: str):
+    """utils/util.py:229-243."""
+    import json
+    prefix = "ann_ndcg_"
+    if not os.path.exists(ann_data_path):
+        return -1, None, None
+    files = list(next(os.walk(ann_data_path))[2])
+    nos = [int(s[len(prefix):]) for s in files if s[:len(prefix)] == prefix and s[len(prefix):].isdigit()]
+    if len(nos) > 0:
+        no = max(nos)
+        with open(os.path.join(ann_data_path, prefix + str(no)), "r") as f:
+            ndcg_json = json.load(f)
+        return no, os.path.join(ann_data_path, "ann_training_data_" + str(no)), ndcg_json
+    return -1, None, None
+
+
+def is_first_worker() -> bool:
+    """utils/util.py:216-217."""
+    return not dist.is_available() or not dist.is_initialized() or dist.get_rank() == 0
+
+
+def _world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def get_latest_checkpoint(args):
+    """run_ann_data_gen.py:55-71: newest `checkpoint-N` dir that already holds scheduler.pt."""
+    if not os.path.exists(args.training_dir):
+        return args.init_model_dir, 0
+    subdirectories = list(next(os.walk(args.training_dir))[1])
+    nums = [get_checkpoint_no(s) for s in subdirectories
+            if os.path.exists(os.path.join(args.training_dir, s, "scheduler.pt"))]
+    if len(nums) > 0:
+        return os.path.join(args.training_dir, "checkpoint-" + str(max(nums))) + "/", max(nums)
+    return args.init_model_dir, 0
+
+
+def load_positive_ids(args):
+    """run_ann_data_gen.py:74-100."""
+    training_query_positive_id: Dict[int, int] = {}
+    with open(os.path.join(args.data_dir, "train-qrel.tsv"), "r", encoding="utf8") as f:
+        for [topicid, docid, rel] in csv.reader(f, delimiter="\t"):
+            assert rel == "1"
+            training_query_positive_id[int(topicid)] = int(docid)
+    dev_query_positive_id: Dict[int, Dict[int, int]] = {}
+    with open(os.path.join(args.data_dir, "dev-qrel.tsv"), "r", encoding="utf8") as f:
+        for [topicid, docid, rel] in csv.reader(f, delimiter="\t"):
+            dev_query_positive_id.setdefault(int(topicid), {})[int(docid)] = int(rel)
+    return training_query_positive_id, dev_query_positive_id
+
+
+# =============================================================================================
+# model + encoding
+# =============================================================================================
+def load_model(args, checkpoint_path):
+    """run_ann_data_gen.py:103-136.  No DDP wrapper: every rank loads the checkpoint itself (the
+    reference wraps only to get `.module`); the tokenizer is never used on this path."""
+    args.model_type = args.model_type.lower()
+    configObj = MSMarcoConfigDict[args.model_type]
+    args.model_name_or_path = checkpoint_path
+    config = configObj.config_class.from_pretrained(
+        args.config_name if args.config_name else args.model_name_or_path, num_labels=2, finetuning_task="MSMarco",
+        cache_dir=args.cache_dir if args.cache_dir else None)
+    model = configObj.model_class.from_pretrained(
+        args.model_name_or_path, from_tf=bool(".ckpt" in args.model_name_or_path), config=config,
+        cache_dir=args.cache_dir if args.cache_dir else None)
+    model.to(args.device)
+    model.eval()
+    return config, None, model
+
+
+def rows_from_batches(emb: torch.Tensor, idx: np.ndarray, batch: int) -> Tuple[torch.Tensor, np.ndarray]:
+    """[n, C, d] chunk embeddings of n consecutive local records -> the reference's row layout:
+    per `batch` documents, chunk-major (run_ann_data_gen.py:183-186)."""
+    n, C, d = emb.shape
+    rows, ids = [], []
+    full = (n // batch) * batch
+    if full:
+        e = emb[:full].reshape(full // batch, batch, C, d).permute(0, 2, 1, 3).reshape(full * C, d)
+        i = np.broadcast_to(idx[:full].reshape(full // batch, 1, batch), (full // batch, C, batch)).reshape(-1)
+        rows.append(e)
+        ids.append(i)
+    if full < n:
+        r = n - full
+        rows.append(emb[full:].permute(1, 0, 2).reshape(r * C, d))
+        ids.append(np.broadcast_to(idx[full:][None, :], (C, r)).reshape(-1))
+    return torch.cat(rows, dim=0), np.concatenate(ids)
+
+
+class B200Backend:
+    """Encode + search on this rank's GPU through libance_b200."""
+
+    def __init__(self, args, model):
+        self.args = args
+        self.model = model
+        self.device = args.device
+
+    def encode(self, cache_path: str, is_query: bool) -> Tuple[torch.Tensor, np.ndarray]:
+        """This rank's records of one token cache -> (rows [n_rows, 768] fp32 CUDA, embedding2id int64)."""
+        args = self.args
+        W, rank = _world()
+        cache = EmbeddingCache(cache_path)
+        L = cache.embedding_size
+        multi = (not is_query) and hasattr(self.model, "encode_lens_multi_chunk") and L > 512
+        B = args.per_gpu_eval_batch_size
+        per = max(B, (args.encode_batch_tokens // L) // B * B)  # super-batch, a multiple of the reference batch
+        reader = StridedBatchReader(cache, per, rank=rank, world_size=W)
+        outs: List[torch.Tensor] = []
+        ids_out: List[np.ndarray] = []
+        with torch.no_grad():
+            for ids, lens, idx in reader:
+                ids_d = ids.to(self.device, non_blocking=True)
+                lens_d = lens.to(self.device, non_blocking=True)
+                if multi:
+                    e = self.model.encode_lens_multi_chunk(ids_d, lens_d)
+                    e, i = rows_from_batches(e, idx.numpy(), B)
+                else:
+                    e, i = self.model.encode_lens(ids_d, lens_d), idx.numpy()
+                outs.append(e)
+                ids_out.append(i)
+        if outs:
+            return torch.cat(outs, dim=0), np.concatenate(ids_out)
+        return torch.empty((0, 768), dtype=torch.float32, device=self.device), np.empty((0,), dtype=np.int64)
+
+    def make_local_search(self, passages: torch.Tensor) -> Callable:
+        from ..search import IndexFlatIP
+        index = IndexFlatIP(passages.shape[1], capacity=max(1, passages.shape[0]), device=self.device,
+                            operand=self.args.search_operand)
+        index.add(passages)
+        return lambda q, k, row_offset: index.search_device(q, k, row_offset=row_offset)
+
+
+# =============================================================================================
+# sharded search: all-gather queries, per-shard top-k, host merge
+# =============================================================================================
+def _shard_sizes(n_local: int, device) -> List[int]:
+    W, _ = _world()
+    if W == 1:
+        return [n_local]
+    t = torch.tensor([n_local], dtype=torch.int64, device=device)
+    out = [torch.zeros_like(t) for _ in range(W)]
+    dist.all_gather(out, t)
+    return [int(x.item()) for x in out]
+
+
+def all_gather_rows(x: torch.Tensor) -> torch.Tensor:
+    """Concatenate every rank's rows in rank order (= the merged order of util.py:129-144)."""
+    W, _ = _world()
+    if W == 1:
+        return x
+    sizes = _shard_sizes(x.shape[0], x.device)
+    mx = max(sizes)
+    pad = torch.zeros((mx, x.shape[1]), dtype=x.dtype, device=x.device)
+    pad[:x.shape[0]] = x
+    out = torch.empty((W * mx, x.shape[1]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, pad)
+    return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(W)], dim=0)
+
+
+def all_gather_ids(ids: np.ndarray, device) -> np.ndarray:
+    t = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)).to(device)
+    return all_gather_rows(t[:, None])[:, 0].cpu().numpy()
+
+
+def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch.Tensor, k: int,
+                   merge_threads: int = 0) -> Optional[np.ndarray]:
+    """Every rank searches its own rows for ALL queries; rank 0 merges.  Returns I [nq, k] (global rows)
+    on rank 0, None elsewhere."""
+    from ..search import merge_topk_host
+    W, rank = _world()
+    sizes = _shard_sizes(n_local_rows, queries_all.device)
+    offset = int(sum(sizes[:rank]))
+    D, I = local_search(queries_all, k, offset)
+    if W == 1:
+        return I.cpu().numpy()
+    if rank == 0:
+        Ds = [torch.empty_like(D) for _ in range(W)]
+        Is = [torch.empty_like(I) for _ in range(W)]
+        dist.gather(D, Ds, dst=0)
+        dist.gather(I, Is, dst=0)
+        _, Im = merge_topk_host([d.cpu().numpy() for d in Ds], [i.cpu().numpy() for i in Is], k, merge_threads)
+        return Im
+    dist.gather(D, None, dst=0)
+    dist.gather(I, None, dst=0)
+    return None
+
+
+# =============================================================================================
+# one refresh
+# =============================================================================================
+def _dump(args, prefix: str, emb: torch.Tensor, emb2id: np.ndarray):
+    """`--inference` dumps under the reference's names (util.py:108-113, run_ann_data_gen.py:213-226)."""
+    _, rank = _world()
+    os.makedirs(args.output_dir, exist_ok=True)
+    np.save(os.path.join(args.output_dir, "{}_emb_p__data_obj_{}.npy".format(prefix, rank)), emb.cpu().numpy(),
+            allow_pickle=False)
+    np.save(os.path.join(args.output_dir, "{}_embid_p__data_obj_{}.npy".format(prefix, rank)), emb2id,
+            allow_pickle=False)
+
+
+def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_id, dev_query_positive_id,
+                     latest_step_num, backend=None):
+    """run_ann_data_gen.py:231-336."""
+    t_start = time.time()
+    if backend is None:
+        _, _, model = load_model(args, checkpoint_path)
+        backend = B200Backend(args, model)
+    step = str(latest_step_num)
+
+    logger.info("***** inference of dev query *****")
+    dev_emb, dev_ids = backend.encode(os.path.join(args.data_dir, "dev-query"), True)
+    logger.info("***** inference of passages *****")
+    p_emb, p_ids = backend.encode(os.path.join(args.data_dir, "passages"), False)
+    logger.info("***** Done passage inference *****")
+    if args.inference:
+        _dump(args, "dev_query_" + step + "_", dev_emb, dev_ids)
+        _dump(args, "passage_" + step + "_", p_emb, p_ids)
+        return None
+    logger.info("***** inference of train query *****")
+    q_emb, q_ids = backend.encode(os.path.join(args.data_dir, "train-query"), True)
+    t_enc = time.time()
+
+    device = p_emb.device
+    local_search = backend.make_local_search(p_emb)
+    passage_embedding2id = all_gather_ids(p_ids, device)
+    dev_all, dev_query_embedding2id = all_gather_rows(dev_emb), all_gather_ids(dev_ids, device)
+    q_all, query_embedding2id = all_gather_rows(q_emb), all_gather_ids(q_ids, device)
+
+    dev_I = sharded_search(local_search, p_emb.shape[0], dev_all, 100)               # run_ann_data_gen.py:276
+    q_start, q_end = postprocess.query_chunk(q_all.shape[0], output_num, args.ann_chunk_factor)
+    q_all, query_embedding2id = q_all[q_start:q_end], query_embedding2id[q_start:q_end]
+    logger.info("Chunked {} query from {}".format(q_end - q_start, q_emb.shape[0]))
+    I = sharded_search(local_search, p_emb.shape[0], q_all.contiguous(), args.topk_training)  # :303
+    t_search = time.time()
+    if not is_first_worker():
+        return None
+
+    dev_ndcg, num_queries_dev = postprocess.eval_dev_query(dev_query_embedding2id, passage_embedding2id,
+                                                           dev_query_positive_id, dev_I)
+    print("Rank:" + str(getattr(args, "rank", 0)) + " --- ANN NDCG@10:" + str(dev_ndcg))
+    sampler = "reference" if args.reference_sampling else "fast"
+    negatives, mrr, nq = postprocess.generate_negatives(
+        query_embedding2id, passage_embedding2id, training_query_positive_id, I, args.negative_sample,
+        select_topk=args.ann_measure_topk_mrr, sampler=sampler, seed=args.seed)
+    if args.ann_measure_topk_mrr:
+        print("Rank:" + str(getattr(args, "rank", 0)) + " --- ANN MRR:" + str(mrr / max(nq, 1)))
+    logger.info("***** Construct ANN Triplet *****")
+    os.makedirs(args.output_dir, exist_ok=True)
+    postprocess.write_training_data(os.path.join(args.output_dir, "ann_training_data_" + str(output_num)),
+                                    query_embedding2id, training_query_positive_id, negatives, sampler=sampler,
+                                    seed=args.seed)
+    postprocess.write_ndcg(os.path.join(args.output_dir, "ann_ndcg_" + str(output_num)), dev_ndcg, checkpoint_path)
+    logger.info("refresh %d: encode %.1fs search %.1fs post %.1fs", output_num, t_enc - t_start, t_search - t_enc,
+                time.time() - t_search)
+    return dev_ndcg, num_queries_dev
+
+
+# =============================================================================================
+# CLI (flags of run_ann_data_gen.py:443-627, plus three B200 knobs at the end)
+# =============================================================================================
+def get_arguments(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--data_dir", default=None, type=str, required=True)
+    p.add_argument("--training_dir", default=None, type=str, required=True)
+    p.add_argument("--init_model_dir", default=None, type=str, required=True)
+    p.add_argument("--last_checkpoint_dir", default="", type=str)
+    p.add_argument("--model_type", default=None, type=str, required=True,
+                   help="Model type selected in the list: " + ", ".join(MSMarcoConfigDict.keys()))
+    p.add_argument("--output_dir", default=None, type=str, required=True)
+    p.add_argument("--cache_dir", default=None, type=str, required=True)
+    p.add_argument("--end_output_num", default=-1, type=int)
+    p.add_argument("--max_seq_length", default=128, type=int)
+    p.add_argument("--max_query_length", default=64, type=int)
+    p.add_argument("--max_doc_character", default=10000, type=int)
+    p.add_argument("--per_gpu_eval_batch_size", default=128, type=int)
+    p.add_argument("--ann_chunk_factor", default=5, type=int)
+    p.add_argument("--topk_training", default=500, type=int)
+    p.add_argument("--negative_sample", default=5, type=int)
+    p.add_argument("--ann_measure_topk_mrr", default=False, action="store_true")
+    p.add_argument("--only_keep_latest_embedding_file", default=False, action="store_true")
+    p.add_argument("--no_cuda", action="store_true")
+    p.add_argument("--local_rank", type=int, default=-1)
+    p.add_argument("--server_ip", type=str, default="")
+    p.add_argument("--server_port", type=str, default="")
+    p.add_argument("--inference", default=False, action="store_true")
+    p.add_argument("--config_name", default="", type=str)
+    p.add_argument("--tokenizer_name", default="", type=str)
+    # B200 knobs (not in the reference)
+    p.add_argument("--search_operand", default="bf16", choices=["bf16", "fp16"],
+                   help="16-bit operand format of the coarse tensor-core pass (results are exact either way)")
+    p.add_argument("--encode_batch_tokens", default=65536, type=int, help="tokens per encoder launch sequence")
+    p.add_argument("--reference_sampling", default=False, action="store_true",
+                   help="draw the negative-sampling order from Python's `random` exactly as the reference does")
+    p.add_argument("--seed", default=None, type=int, help="seed for the sampling order (reference: unseeded)")
+    p.add_argument("--poll_seconds", default=60, type=int)
+    return p.parse_args(argv)
+
+
+def set_env(args):
+    """run_ann_data_gen.py:630-660.  torchrun exports LOCAL_RANK; the legacy launcher passes --local_rank."""
+    if args.local_rank == -1 and "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        args.local_rank = int(os.environ["LOCAL_RANK"])
+    if args.no_cuda or not torch.cuda.is_available():
+        raise RuntimeError("ance_b200 has no CPU fallback: the refresher needs an sm_100 GPU (drop --no_cuda)")
+    if args.local_rank == -1:
+        args.device = torch.device("cuda", torch.cuda.current_device())
+        args.n_gpu = 1
+    else:
+        torch.cuda.set_device(args.local_rank)
+        args.device = torch.device("cuda", args.local_rank)
+        if not dist.is_initialized():
+            dist.init_process_group(backend="nccl")
+        args.n_gpu = 1
+        args.world_size = dist.get_world_size()
+    args.rank = _world()[1]
+    logging.basicConfig(format="%(asctime)s - %(levelname)s - %(name)s -   %(message)s", datefmt="%m/%d/%Y %H:%M:%S",
+                        level=logging.INFO if args.local_rank in [-1, 0] else logging.WARN)
+    if args.seed is not None:
+        random.seed(args.seed)
+
+
+def ann_data_gen(args, backend=None):
+    """run_ann_data_gen.py:663-702."""
+    last_checkpoint = args.last_checkpoint_dir
+    ann_no, _, _ = get_latest_ann_data(args.output_dir)
+    output_num = ann_no + 1
+    logger.info("starting output number %d", output_num)
+    if is_first_worker():
+        os.makedirs(args.output_dir, exist_ok=True)
+        os.makedirs(args.cache_dir, exist_ok=True)
+    training_positive_id, dev_positive_id = load_positive_ids(args)
+    while args.end_output_num == -1 or output_num <= args.end_output_num:
+        next_checkpoint, latest_step_num = get_latest_checkpoint(args)
+        if args.only_keep_latest_embedding_file:
+            latest_step_num = 0
+        if next_checkpoint == last_checkpoint:
+            time.sleep(args.poll_seconds)
+        else:
+            logger.info("start generate ann data number %d", output_num)
+            logger.info("next checkpoint at " + next_checkpoint)
+            generate_new_ann(args, output_num, next_checkpoint, training_positive_id, dev_positive_id, latest_step_num,
+                             backend=backend)
+            if args.inference:
+                break
+            logger.info("finished generating ann data number %d", output_num)
+            output_num += 1
+            last_checkpoint = next_checkpoint
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+
+
+def main(argv=None):
+    args = get_arguments(argv)
+    set_env(args)
+    ann_data_gen(args)
+
+
+if __name__ == "__main__":
+    main()

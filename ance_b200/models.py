@@ -141,6 +141,17 @@ class _CudaEncoder:
         except Exception:
             pass
 
+    def enable_debug(self):
+        """Capture hidden states of batches up to 4096 tokens (parity tests only)."""
+        _lib.check(self.lib.ance_encoder_debug_hidden(self.h, -1, None, None))
+
+    def hidden(self, layer: int, n_tokens: int) -> torch.Tensor:
+        """Hidden states after `layer` (0 = embeddings) of the last forward, fp32 [n_tokens, H]."""
+        buf = torch.empty((min(self.max_tokens, 4096), self.hidden), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ance_encoder_debug_hidden(self.h, layer, buf.data_ptr(), _lib.current_stream()))
+        return buf[:n_tokens]
+
     def forward(self, ids: torch.Tensor, lens: Optional[torch.Tensor], mask: Optional[torch.Tensor]) -> torch.Tensor:
         """ids int32 [B, L] CUDA; exactly one of lens int32 [B] / mask uint8 [B, L].  -> fp32 [B, H]."""
         B, L = ids.shape

@@ -1,0 +1,165 @@
+"""Host-side post-processing of one ANN refresh: negatives, dev NDCG, output files.
+
+Same results as the reference's pure-Python loops
+  * GenerateNegativePassaageID   drivers/run_ann_data_gen.py:339-396
+  * EvalDevQuery                 drivers/run_ann_data_gen.py:399-440
+  * the writers                  drivers/run_ann_data_gen.py:315-334 (data file first, ann_ndcg json last:
+                                 the trainer discovers a version by the json, utils/util.py:229-243)
+but vectorised with numpy (the O(nq*k) Python loop with `in list` membership is the longest serial
+segment of a refresh once encode and search run on the GPU).
+
+Sampling order.  The reference visits each query's k neighbours in an order drawn from the
+module-level, unseeded `random`.  `sampler="reference"` consumes Python's `random` exactly as the
+reference does (same calls, same order), so under `random.seed(s)` the output files are byte-identical
+to the reference's; `sampler="fast"` draws all permutations at once from a numpy Generator.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import random
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def _first_occurrence(pids: np.ndarray) -> np.ndarray:
+    """mask[r, j] = True iff pids[r, j] does not appear in pids[r, :j]."""
+    n, m = pids.shape
+    order = np.argsort(pids, axis=1, kind="stable")
+    sp = np.take_along_axis(pids, order, axis=1)
+    first_sorted = np.ones((n, m), dtype=bool)
+    first_sorted[:, 1:] = sp[:, 1:] != sp[:, :-1]
+    first = np.empty((n, m), dtype=bool)
+    np.put_along_axis(first, order, first_sorted, axis=1)
+    return first
+
+
+def generate_negatives(query_embedding2id: np.ndarray, passage_embedding2id: np.ndarray, positives: Dict[int, int],
+                       I: np.ndarray, negative_sample: int, select_topk: bool = False, sampler: str = "fast",
+                       seed: Optional[int] = None) -> Tuple[Dict[int, List[int]], float, int]:
+    """-> ({qid: [neg pids]}, mrr_sum, num_queries).  `I` holds global passage ROWS (faiss labels);
+    every query of `query_embedding2id` is effective (the reference builds effective_q_id from the same
+    array, run_ann_data_gen.py:305)."""
+    nq, k = I.shape
+    qids = np.asarray(query_embedding2id).reshape(-1).astype(np.int64)
+    if nq == 0:
+        return {}, 0.0, 0
+    pos = np.fromiter((positives[int(q)] for q in qids), dtype=np.int64, count=nq)  # KeyError like the reference
+    if select_topk:
+        sel = I[:, :negative_sample + 1]
+    elif sampler == "reference":
+        perm = np.empty((nq, k), dtype=np.int64)
+        base = list(range(k))
+        for r in range(nq):
+            p = base.copy()
+            random.shuffle(p)
+            perm[r] = p
+        sel = np.take_along_axis(I, perm, axis=1)
+    elif sampler == "fast":
+        rng = np.random.default_rng(seed)
+        perm = rng.permuted(np.broadcast_to(np.arange(k), (nq, k)), axis=1)
+        sel = np.take_along_axis(I, perm, axis=1)
+    else:
+        raise ValueError(f"unknown sampler {sampler!r}")
+    if (sel < 0).any():
+        raise IndexError("search returned -1 labels (fewer rows than k); the reference would index "
+                         "passage_embedding2id[-1] silently — refusing")
+    pids = np.asarray(passage_embedding2id).reshape(-1)[sel]
+    is_pos = pids == pos[:, None]
+    valid = _first_occurrence(pids) & ~is_pos
+    csum = np.cumsum(valid, axis=1)
+    take = valid & (csum <= negative_sample)
+    # the reference's loop breaks at the first valid candidate met once negative_sample were taken
+    brk_mask = valid & (csum == negative_sample + 1)
+    m = sel.shape[1]
+    brk = np.where(brk_mask.any(axis=1), brk_mask.argmax(axis=1), m)
+    ranks = np.arange(1, m + 1)[None, :]
+    hit = is_pos & (ranks <= 10) & (np.arange(m)[None, :] < brk[:, None])
+    mrr = float((hit / ranks).sum())
+    out: Dict[int, List[int]] = {}
+    for r in range(nq):
+        out[int(qids[r])] = pids[r, take[r]].tolist()
+    return out, mrr, nq
+
+
+def ndcg_cut(ranked_pids: Sequence[int], qrel: Dict[int, int], cut: int = 10) -> float:
+    """trec_eval's ndcg_cut_k (what the reference reads from pytrec_eval, run_ann_data_gen.py:426-435):
+    gain = relevance, discount = log2(rank + 1), ideal from all judged documents of the query."""
+    dcg = 0.0
+    for r, pid in enumerate(ranked_pids[:cut], start=1):
+        g = qrel.get(int(pid), 0)
+        if g > 0:
+            dcg += g / math.log2(r + 1)
+    ideal = sorted((g for g in qrel.values() if g > 0), reverse=True)[:cut]
+    idcg = sum(g / math.log2(r + 1) for r, g in enumerate(ideal, start=1))
+    return dcg / idcg if idcg > 0 else 0.0
+
+
+def eval_dev_query(query_embedding2id: np.ndarray, passage_embedding2id: np.ndarray,
+                   dev_query_positive_id: Dict[int, Dict[int, int]], I: np.ndarray) -> Tuple[float, int]:
+    """Mean ndcg_cut_10 over the dev queries that have qrels, from the first 50 neighbours with
+    pid de-duplication (run_ann_data_gen.py:413-423).  -> (ndcg, evaluated query count)."""
+    top = I[:, :50]
+    if top.size and (top < 0).any():
+        raise IndexError("search returned -1 labels (fewer rows than k)")
+    pids = np.asarray(passage_embedding2id).reshape(-1)[top]
+    first = _first_occurrence(pids) if pids.size else np.zeros_like(pids, dtype=bool)
+    pred: Dict[int, np.ndarray] = {}
+    qids = np.asarray(query_embedding2id).reshape(-1)
+    for r in range(top.shape[0]):
+        pred[int(qids[r])] = pids[r, first[r]]  # duplicate qids: last wins, as the dict assignment does
+    total, n = 0.0, 0
+    for qid, ranked in pred.items():
+        qrel = dev_query_positive_id.get(qid)
+        if qrel is None:
+            continue
+        n += 1
+        total += ndcg_cut(ranked, qrel, 10)
+    if n == 0:
+        raise ZeroDivisionError("no dev query has a qrel (the reference divides by zero here too)")
+    return total / n, n
+
+
+def write_training_data(path: str, query_embedding2id: np.ndarray, positives: Dict[int, int],
+                        negatives: Dict[int, List[int]], sampler: str = "fast", seed: Optional[int] = None) -> int:
+    """`qid \\t pos_pid \\t n1,n2,...` per query, in shuffled query order (run_ann_data_gen.py:318-329).
+    Returns the number of lines."""
+    qids = np.asarray(query_embedding2id).reshape(-1)
+    order = list(range(len(qids)))
+    if sampler == "reference":
+        random.shuffle(order)
+    else:
+        order = np.random.default_rng(None if seed is None else seed + 1).permutation(len(qids)).tolist()
+    n = 0
+    tmp = path + ".tmp"
+    with open(tmp, "w") as f:
+        for qi in order:
+            qid = int(qids[qi])
+            if qid not in positives or qid not in negatives:
+                continue
+            f.write("{}\t{}\t{}\n".format(qid, positives[qid], ",".join(str(p) for p in negatives[qid])))
+            n += 1
+    os.replace(tmp, path)  # a reader never sees a partial file (the reference writes in place)
+    return n
+
+
+def write_ndcg(path: str, ndcg: float, checkpoint: str) -> None:
+    """run_ann_data_gen.py:331-334 — written AFTER the data file."""
+    tmp = path + ".tmp"
+    with open(tmp, "w") as f:
+        json.dump({"ndcg": ndcg, "checkpoint": checkpoint}, f)
+    os.replace(tmp, path)
+
+
+def query_chunk(num_queries: int, output_num: int, chunk_factor: int) -> Tuple[int, int]:
+    """run_ann_data_gen.py:281-296.  The reference evaluates `output_num % chunk_factor` before its
+    `chunk_factor <= 0` guard (ZeroDivisionError for 0); here 0 / negative mean 'one chunk'."""
+    if chunk_factor <= 0:
+        chunk_factor = 1
+    effective = output_num % chunk_factor
+    per = num_queries // chunk_factor
+    start = per * effective
+    end = num_queries if effective == chunk_factor - 1 else start + per
+    return start, end

@@ -68,8 +68,10 @@ def child(N, nq, k, fmt, cg, kind, check, kprime):
             bad = (Si[:, :k] != Ie[:nref]).sum().item()
             res["exact_I_mismatch_count"] = bad
             res["exact_D_maxdiff"] = (Ss[:, :k] - De[:nref]).abs().max().item()
+    print("data+index ready", time.time(), file=sys.stderr, flush=True)
     D, I = idx.search_device(Q, k)
     torch.cuda.synchronize()
+    print("first search done", time.time(), file=sys.stderr, flush=True)
     st = idx.stats()
     res["stats"] = st
     if check:
@@ -113,6 +115,10 @@ def main():
         (1000000, 37888, 200, 1, 2, "clustered", 0, 0),
         (8841823, 37888, 200, 1, 1, "clustered", 0, 0),
         (8841823, 6980, 100, 1, 1, "clustered", 0, 0),
+        (2000000, 37888, 200, 1, 1, "clustered", 0, 0),
+        (4000000, 37888, 200, 1, 1, "clustered", 0, 0),
+        (8841823, 18944, 200, 1, 1, "clustered", 0, 0),
+        (8841823, 37888, 200, 1, 1, "iid", 0, 0),
     ]
     if len(sys.argv) > 1:
         cases = [cases[int(i)] for i in sys.argv[1].split(",")]
@@ -121,7 +127,7 @@ def main():
             t0 = time.time()
             try:
                 r = subprocess.run([sys.executable, __file__, "child", *map(str, c)], capture_output=True, text=True,
-                                   timeout=400)
+                                   timeout=240)
                 line = (r.stdout.strip().splitlines() or ["{}"])[-1]
                 try:
                     res = json.loads(line)
@@ -131,8 +137,9 @@ def main():
                 if r.returncode != 0:
                     res["stderr"] = r.stderr[-2500:]
                     res["stdout"] = r.stdout[-1500:]
-            except subprocess.TimeoutExpired:
-                res = {"ok": False, "timeout": True}
+            except subprocess.TimeoutExpired as e:
+                err = e.stderr.decode("utf-8", "replace") if isinstance(e.stderr, bytes) else str(e.stderr)
+                res = {"ok": False, "timeout": True, "stderr": err[-2000:]}
             res["case"] = c
             res["wall_s"] = round(time.time() - t0, 1)
             print(json.dumps(res), flush=True)
