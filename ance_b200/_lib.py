@@ -24,6 +24,7 @@ class AnceError(RuntimeError):
 class SearchStats(C.Structure):
     _fields_ = [
         ("nq", C.c_int64),
+        ("n_tier2", C.c_int64),
         ("n_uncertified", C.c_int64),
         ("n_candidates", C.c_int64),
         ("kprime", C.c_int32),
@@ -76,6 +77,8 @@ SIGNATURES = {
     "ance_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p]),
     "ance_encoder_debug_hidden": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ance_profile_enable": (C.c_int, [C.c_int]),
+    "ance_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int, C.c_int]),
     "ance_dbg_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                 C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -119,3 +122,19 @@ def ptr(t) -> int:
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+PROFILE_CLASSES = ("encoder_gemm", "attention", "norm_embed", "quantize", "coarse_search", "rescore", "exact")
+
+
+def profile_enable(on: bool = True) -> None:
+    check(load().ance_profile_enable(1 if on else 0))
+
+
+def profile_read(reset: bool = True) -> dict:
+    """{class: (milliseconds, launches)} of device time since the last reset (synchronises)."""
+    n = len(PROFILE_CLASSES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(load().ance_profile_read(ms, cnt, n, 1 if reset else 0))
+    return {PROFILE_CLASSES[i]: (ms[i], cnt[i]) for i in range(n)}

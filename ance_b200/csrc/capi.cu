@@ -1,6 +1,8 @@
 // capi.cu — error state, version, launch counter and the bring-up GEMM hook of libance_b200.so.
 #include <atomic>
+#include <mutex>
 #include <string.h>
+#include <vector>
 
 #include "common.h"
 #include "gemm_store.cuh"
@@ -19,11 +21,63 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- profile ----
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::vector<cudaEvent_t> g_ev_pool;
+struct Span { cudaEvent_t a, b; };
+static std::vector<Span> g_spans[kNumCls];
+static cudaEvent_t g_open[kNumCls];
+static double g_ms[kNumCls];
+static int64_t g_cnt[kNumCls];
+
+static cudaEvent_t get_event() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_open[cls] = get_event();
+  cudaEventRecord(g_open[cls], st);
+}
+void prof_end(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t b = get_event();
+  cudaEventRecord(b, st);
+  g_spans[cls].push_back({g_open[cls], b});
+}
+
 }  // namespace ance
 
 extern "C" const char* ance_version(void) { return "ance_b200 0.1 (sm_100a)"; }
 extern "C" const char* ance_last_error(void) { return ance::g_err; }
 extern "C" int64_t ance_launch_count(void) { return ance::g_launches.load(); }
+
+extern "C" int ance_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(ance::g_prof_mu);
+  ance::g_prof_on = on != 0;
+  return ANCE_OK;
+}
+
+extern "C" int ance_profile_read(double* ms_by_class, int64_t* launches_by_class, int n, int reset) {
+  ANCE_REQUIRE(ms_by_class && launches_by_class && n > 0 && n <= ance::kNumCls, "ance_profile_read: bad arguments");
+  ANCE_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(ance::g_prof_mu);
+  for (int c = 0; c < ance::kNumCls; ++c) {
+    for (auto& s : ance::g_spans[c]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { ance::g_ms[c] += ms; ance::g_cnt[c] += 1; }
+      ance::g_ev_pool.push_back(s.a);
+      ance::g_ev_pool.push_back(s.b);
+    }
+    ance::g_spans[c].clear();
+  }
+  for (int c = 0; c < n; ++c) { ms_by_class[c] = ance::g_ms[c]; launches_by_class[c] = ance::g_cnt[c]; }
+  if (reset) for (int c = 0; c < ance::kNumCls; ++c) { ance::g_ms[c] = 0; ance::g_cnt[c] = 0; }
+  return ANCE_OK;
+}
 
 namespace {
 

@@ -9,6 +9,17 @@
 namespace ance {
 
 void set_error(const char* fmt, ...);  // defined in capi.cu
+void count_launch(int n);
+
+// device-time profile by kernel class (see ance_profile_enable in the header)
+enum KernelClass { kClsGemm = 0, kClsAttn = 1, kClsNorm = 2, kClsQuant = 3, kClsCoarse = 4, kClsRescore = 5, kClsExact = 6, kNumCls = 8 };
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(int cls, cudaStream_t st);
+struct ProfScope {
+  int cls; cudaStream_t st;
+  ProfScope(int c, cudaStream_t s) : cls(c), st(s) { prof_begin(cls, st); }
+  ~ProfScope() { prof_end(cls, st); }
+};
 
 #define ANCE_CUDA(expr)                                                                       \
   do {                                                                                        \

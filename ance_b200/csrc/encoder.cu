@@ -21,10 +21,6 @@
 #include "common.h"
 #include "gemm_store.cuh"
 
-namespace ance {
-void count_launch(int n);
-}
-
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -290,7 +286,10 @@ int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, in
   p.ldc32 = N;
   p.ldr = N;
   p.act = act;
-  ANCE_CUDA((gemm::launch<Ep, BN, 4, 1, EW, tc05::kFmtBF16>(tmA, tmB, ws, p, 0, st)));
+  {
+    ance::ProfScope ps(ance::kClsGemm, st);
+    ANCE_CUDA((gemm::launch<Ep, BN, 4, 1, EW, tc05::kFmtBF16>(tmA, tmB, ws, p, 0, st)));
+  }
   ance::count_launch(1);
   return ANCE_OK;
 }
@@ -299,6 +298,7 @@ int layer_norm(const void* in, bool in_f32, size_t in_ld, int rows, int H, const
                __nv_bfloat16* out16, float* out32, cudaStream_t st) {
   const int blocks = (rows + 7) / 8;
   const int nv = H / 256;
+  ance::ProfScope ps(ance::kClsNorm, st);
 #define LN_CASE(NV_)                                                                                       \
   if (in_f32) ln_rows_kernel<NV_, true><<<blocks, 256, 0, st>>>(in, in_ld, rows, H, g, b, eps, out16, out32); \
   else ln_rows_kernel<NV_, false><<<blocks, 256, 0, st>>>(in, in_ld, rows, H, g, b, eps, out16, out32)
@@ -428,12 +428,14 @@ extern "C" int ance_encoder_forward(ance_encoder_t e, const int32_t* ids_dev, co
   ep.word = e->word; ep.pos = e->pos; ep.type = e->type;
   ep.gamma = e->eg; ep.beta = e->eb; ep.eps = c.ln_eps;
   ep.X = e->X; ep.kbias = e->kbias; ep.err_flag = e->err_flag;
+  ance::prof_begin(ance::kClsNorm, st);
   switch (H / 256) {
     case 1: embed_ln_kernel<1><<<B, 256, 0, st>>>(ep); break;
     case 2: embed_ln_kernel<2><<<B, 256, 0, st>>>(ep); break;
     case 3: embed_ln_kernel<3><<<B, 256, 0, st>>>(ep); break;
     default: embed_ln_kernel<4><<<B, 256, 0, st>>>(ep); break;
   }
+  ance::prof_end(ance::kClsNorm, st);
   ANCE_CUDA(cudaGetLastError());
   ance::count_launch(1);
   if (e->dbg && M <= e->dbg_tokens) ANCE_CUDA(cudaMemcpyAsync(e->dbg, e->X, static_cast<size_t>(M) * H * 2, cudaMemcpyDeviceToDevice, st));
@@ -452,7 +454,9 @@ extern "C" int ance_encoder_forward(ance_encoder_t e, const int32_t* ids_dev, co
   for (int l = 0; l < c.n_layer; ++l) {
     const LayerDev& d = e->layers[l];
     if ((rc = linear(e->X, H, M, d.wqkv, 3 * H, H, d.bqkv, nullptr, 0, e->QKV, nullptr, st))) return rc;
+    ance::prof_begin(ance::kClsAttn, st);
     attn::attention_kernel<<<attn_grid, 256, attn::Smem::kDynamic, st>>>(tmQKV, ap);
+    ance::prof_end(ance::kClsAttn, st);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(1);
     if ((rc = linear(e->CTX, H, M, d.wo, H, H, d.bo, e->X, 0, e->T, nullptr, st))) return rc;
@@ -469,6 +473,7 @@ extern "C" int ance_encoder_forward(ance_encoder_t e, const int32_t* ids_dev, co
     if ((rc = linear(e->X, static_cast<size_t>(L) * H, B, e->head_w, H, H, e->head_b, nullptr, 0, nullptr, e->head_tmp, st))) return rc;
     if ((rc = layer_norm(e->head_tmp, true, H, B, H, e->head_g, e->head_bt, 1e-5f, nullptr, out_dev, st))) return rc;
   } else {
+    ance::ProfScope ps(ance::kClsNorm, st);
     gather_rows_f32_kernel<<<B, 256, 0, st>>>(e->X, static_cast<size_t>(L) * H, B, H, out_dev);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(1);

@@ -26,10 +26,6 @@
 #include "common.h"
 #include "gemm_core.cuh"
 
-namespace ance {
-void count_launch(int n);
-}
-
 namespace {
 
 using namespace tc05;
@@ -340,10 +336,12 @@ struct RescoreParams {
   float* D;
   int64_t* I;
   int64_t row_offset;
-  int* flagged_list;
-  int* counters;   // [0] n_flagged [1] n_candidates
+  const int* qlist;    // block b handles candidate slot b of query qlist[b] (null: query b)
+  int* flagged_list;   // uncertified queries of this pass
+  int flag_slot;       // counters[flag_slot] counts them
+  int* counters;       // [0] tier-1 flagged [1] n_candidates [2] max eps bits [3] tier-2 flagged
   unsigned int* max_eps;
-  int sort_n;      // pow2 >= n_splits * kprime
+  int sort_n;          // pow2 >= n_splits * kprime
 };
 
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
@@ -351,7 +349,8 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   uint64_t* keys = reinterpret_cast<uint64_t*>(rs_smem);
   float* qs = reinterpret_cast<float*>(keys + p.sort_n);
   int* offs = reinterpret_cast<int*>(qs + p.d);  // [n_splits + 1]
-  const int q = blockIdx.x;
+  const int ql = blockIdx.x;                       // slot in the candidate arrays
+  const int q = p.qlist ? p.qlist[ql] : ql;        // query number (rows of Q, D, I)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
   for (int i = threadIdx.x; i < p.d; i += blockDim.x) qs[i] = p.Q[static_cast<size_t>(q) * p.d + i];
@@ -359,7 +358,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     int o = 0;
     for (int s = 0; s < p.n_splits; ++s) {
       offs[s] = o;
-      o += p.cand_cnt[static_cast<size_t>(q) * p.n_splits + s];
+      o += p.cand_cnt[static_cast<size_t>(ql) * p.n_splits + s];
     }
     offs[p.n_splits] = o;
   }
@@ -369,7 +368,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   __syncthreads();
   for (int s = 0; s < p.n_splits; ++s) {
     const int n = offs[s + 1] - offs[s];
-    const int* ids = p.cand_id + (static_cast<size_t>(q) * p.n_splits + s) * p.kprime;
+    const int* ids = p.cand_id + (static_cast<size_t>(ql) * p.n_splits + s) * p.kprime;
     for (int c = warp; c < n; c += nwarps) {
       const int row = ids[c];
       const double dot = warp_dot_f64(qs, p.P + static_cast<size_t>(row) * p.d, p.d, lane);
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   }
   if (threadIdx.x == 0) {
     float thr = -INFINITY;
-    for (int s = 0; s < p.n_splits; ++s) thr = fmaxf(thr, p.cand_thr[static_cast<size_t>(q) * p.n_splits + s]);
+    for (int s = 0; s < p.n_splits; ++s) thr = fmaxf(thr, p.cand_thr[static_cast<size_t>(ql) * p.n_splits + s]);
     const float maxp = __uint_as_float(p.pstats[0]), maxdp = __uint_as_float(p.pstats[1]);
     const float qn = p.qn_hat[q], qd = p.qn_delta[q];
     const float eps = (qd * maxp + qn * maxdp + qd * maxdp + p.accum_rel * qn * maxp) * 1.0001f;
@@ -395,7 +394,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     atomicAdd(&p.counters[1], m);
     atomicMax(p.max_eps, __float_as_uint(eps));
     if (!certified) {
-      const int slot = atomicAdd(&p.counters[0], 1);
+      const int slot = atomicAdd(&p.counters[p.flag_slot], 1);
       p.flagged_list[slot] = q;
     }
   }
@@ -537,6 +536,16 @@ __global__ void __launch_bounds__(256) exact_merge_kernel(const ExactParams p, f
   }
 }
 
+// 16-bit operand rows of the listed queries -> compact matrix (second, wider coarse pass)
+__global__ void gather_rows16_kernel(const uint16_t* __restrict__ src, const int* __restrict__ qlist, int n, int d,
+                                     uint16_t* __restrict__ dst) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(qlist[r]) * d);
+  uint4* o = reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) o[i] = s[i];
+}
+
 __global__ void fill_i32(int* p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -557,12 +566,14 @@ struct ance_index {
   unsigned int* pstats = nullptr;  // [2]
   int* err_flag = nullptr;
   // tunables
-  int kprime = 0, n_splits = 0, cta_group = 1, max_ctas = 0;
+  int kprime = 0, n_splits = 0, cta_group = 1, max_ctas = 0, exact_fallback = 1, tier2 = 1;
   // workspace (grown lazily)
   uint16_t* Q16 = nullptr; float* qn_hat = nullptr; float* qn_delta = nullptr; int64_t q_cap = 0;
   float* scratch_sc = nullptr; int* scratch_id = nullptr; size_t scratch_elems = 0;
   int* cand_id = nullptr; int* cand_cnt = nullptr; float* cand_thr = nullptr; size_t cand_slots = 0, cand_ids = 0;
   int* flagged = nullptr; int64_t flagged_cap = 0;
+  int* flagged2 = nullptr; size_t flagged2_cap = 0;
+  uint16_t* Q16b = nullptr; size_t q16b_elems = 0;
   int* counters = nullptr;          // [4]: n_flagged, n_candidates, max_eps bits, spare
   uint64_t* chunk_keys = nullptr; size_t chunk_keys_elems = 0;
   // last search
@@ -605,13 +616,14 @@ int check_device() {
 }
 
 template <int BN, int STAGES, int CG, int CAP, uint32_t FMT>
-int launch_coarse(ance_index* ix, int64_t nq, int kprime, int n_splits_req, int* n_splits_out, cudaStream_t st) {
+int launch_coarse(ance_index* ix, const uint16_t* Q16, int64_t nq, int kprime, int n_splits_req, int* n_splits_out,
+                  cudaStream_t st) {
   using Ep = EpTopK<BN, CAP>;
   const int N = static_cast<int>(ix->n);
   gemm::WorkShape ws = gemm::make_shape(static_cast<int>(nq), N, ix->dim, BN, CG, n_splits_req);
   *n_splits_out = ws.n_splits;
   CUtensorMap tmA, tmB;
-  if (!tc05_host::make_tmap_2d_16b(&tmA, ix->Q16, nq, ix->dim, ix->dim, gemm::BM) ||
+  if (!tc05_host::make_tmap_2d_16b(&tmA, Q16, nq, ix->dim, ix->dim, gemm::BM) ||
       !tc05_host::make_tmap_2d_16b(&tmB, ix->P16, ix->n, ix->dim, ix->dim, BN / CG)) {
     ance::set_error("cuTensorMapEncodeTiled failed (nq=%lld n=%lld d=%d)", (long long)nq, (long long)ix->n, ix->dim);
     return ANCE_ERR_CUDA;
@@ -639,7 +651,10 @@ int launch_coarse(ance_index* ix, int64_t nq, int kprime, int n_splits_req, int*
   p.kprime = kprime;
   p.nq = static_cast<int>(nq);
   p.n_rows = N;
-  ANCE_CUDA((gemm::launch<Ep, BN, STAGES, CG, 4, FMT>(tmA, tmB, ws, p, ctas, st)));
+  {
+    ance::ProfScope ps(ance::kClsCoarse, st);
+    ANCE_CUDA((gemm::launch<Ep, BN, STAGES, CG, 4, FMT>(tmA, tmB, ws, p, ctas, st)));
+  }
   ance::count_launch(1);
   return ANCE_OK;
 }
@@ -676,12 +691,80 @@ int run_exact(ance_index* ix, const float* Q, const int* qlist, int nq, int k, f
     ep.q_base = b0;
     ep.nq = nb;
     const int gy = std::max(1, std::min((nb + kExQB - 1) / kExQB, 128));
+    ance::ProfScope ps(ance::kClsExact, st);
     exact_chunk_kernel<<<dim3(n_chunks, gy), 256, smem, st>>>(ep);
     ANCE_CUDA(cudaGetLastError());
     exact_merge_kernel<<<std::max(1, std::min(nb, 4 * sms)), 256, 0, st>>>(ep, D, I, k, row_offset);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(2);
   }
+  return ANCE_OK;
+}
+
+// One coarse pass + exact rescoring + certificate over `nq` queries whose 16-bit rows are Q16[0..nq);
+// qlist (or identity) maps them to rows of q_f32 / D / I.  Uncertified queries are appended to
+// flagged_out and counted in counters[flag_slot].
+int coarse_rescore_pass(ance_index* ix, const uint16_t* Q16, const float* q_f32, int64_t nq, const int* qlist,
+                        int kprime, int n_splits_req, int k, float* D_dev, int64_t* I_dev, int64_t row_offset,
+                        int* flagged_out, int flag_slot, int* ns_out, cudaStream_t st) {
+  int rc;
+  const int cap = (kprime <= 512) ? 1024 : 2048;
+  const int cg = ix->cta_group;
+  const int clusters = (ix->max_ctas > 0 ? ix->max_ctas : gemm::sm_count()) / cg;
+  const int q_tiles = static_cast<int>((nq + gemm::BM * cg - 1) / (gemm::BM * cg));
+  int n_splits = n_splits_req;
+  if (n_splits == 0) {
+    // enough work items to fill the machine twice over when there are few query tiles
+    n_splits = (q_tiles >= 2 * clusters) ? 1 : std::min(16, (2 * clusters + q_tiles - 1) / q_tiles);
+  }
+  while (n_splits > 1 && n_splits * kprime > 4096) --n_splits;
+  ANCE_REQUIRE(n_splits * kprime <= 4096, "ance_index_search: n_splits * kprime = %d exceeds 4096", n_splits * kprime);
+  int ns = 0;
+  const bool bf = ix->fmt == ANCE_FMT_BF16;
+#define ANCE_COARSE(CG_, CAP_)                                                                                     \
+  rc = bf ? launch_coarse<256, (CG_ == 1 ? 4 : 6), CG_, CAP_, tc05::kFmtBF16>(ix, Q16, nq, kprime, n_splits, &ns, st) \
+          : launch_coarse<256, (CG_ == 1 ? 4 : 6), CG_, CAP_, tc05::kFmtF16>(ix, Q16, nq, kprime, n_splits, &ns, st)
+  if (cg == 1 && cap == 1024) { ANCE_COARSE(1, 1024); }
+  else if (cg == 1) { ANCE_COARSE(1, 2048); }
+  else if (cap == 1024) { ANCE_COARSE(2, 1024); }
+  else { ANCE_COARSE(2, 2048); }
+#undef ANCE_COARSE
+  if (rc) return rc;
+  *ns_out = ns;
+  RescoreParams rp;
+  rp.Q = q_f32;
+  rp.P = ix->P32;
+  rp.d = ix->dim;
+  rp.cand_id = ix->cand_id;
+  rp.cand_cnt = ix->cand_cnt;
+  rp.cand_thr = ix->cand_thr;
+  rp.n_splits = ns;
+  rp.kprime = kprime;
+  rp.k = k;
+  rp.qn_hat = ix->qn_hat;
+  rp.qn_delta = ix->qn_delta;
+  rp.pstats = ix->pstats;
+  rp.accum_rel = 3.0517578125e-5f;  // 2^-15, see DESIGN.md "certificate"
+  rp.D = D_dev;
+  rp.I = I_dev;
+  rp.row_offset = row_offset;
+  rp.qlist = qlist;
+  rp.flagged_list = flagged_out;
+  rp.flag_slot = flag_slot;
+  rp.counters = ix->counters;
+  rp.max_eps = reinterpret_cast<unsigned int*>(ix->counters + 2);
+  rp.sort_n = next_pow2(ns * kprime);
+  const size_t rs_smem = static_cast<size_t>(rp.sort_n) * 8 + static_cast<size_t>(ix->dim) * 4 + (ns + 1) * 4 + 16;
+  static size_t rs_attr = 0;
+  if (rs_smem > 48 * 1024 && rs_smem > rs_attr) {
+    ANCE_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem)));
+    rs_attr = rs_smem;
+  }
+  ance::prof_begin(ance::kClsRescore, st);
+  rescore_kernel<<<static_cast<unsigned>(nq), 256, rs_smem, st>>>(rp);
+  ance::prof_end(ance::kClsRescore, st);
+  ANCE_CUDA(cudaGetLastError());
+  ance::count_launch(1);
   return ANCE_OK;
 }
 
@@ -720,7 +803,8 @@ extern "C" int ance_index_create(int dim, int64_t capacity_rows, int operand_fmt
 extern "C" int ance_index_destroy(ance_index_t ix) {
   if (!ix) return ANCE_OK;
   void* ptrs[] = {ix->P32, ix->P16, ix->pstats, ix->err_flag, ix->Q16, ix->qn_hat, ix->qn_delta, ix->scratch_sc,
-                  ix->scratch_id, ix->cand_id, ix->cand_cnt, ix->cand_thr, ix->flagged, ix->counters, ix->chunk_keys};
+                  ix->scratch_id, ix->cand_id, ix->cand_cnt, ix->cand_thr, ix->flagged, ix->counters, ix->chunk_keys,
+                  ix->flagged2, ix->Q16b};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ix;
@@ -766,6 +850,8 @@ extern "C" int ance_index_set_param(ance_index_t ix, const char* name, double va
   if (!strcmp(name, "kprime")) { ANCE_REQUIRE(v >= 0 && v <= 1024 && v % 32 == 0, "kprime must be a multiple of 32 in [0, 1024]"); ix->kprime = v; }
   else if (!strcmp(name, "n_splits")) { ANCE_REQUIRE(v >= 0 && v <= 64, "n_splits must be in [0, 64]"); ix->n_splits = v; }
   else if (!strcmp(name, "cta_group")) { ANCE_REQUIRE(v == 1 || v == 2, "cta_group must be 1 or 2"); ix->cta_group = v; }
+  else if (!strcmp(name, "exact_fallback")) { ix->exact_fallback = v != 0; }
+  else if (!strcmp(name, "tier2")) { ix->tier2 = v != 0; }
   else if (!strcmp(name, "max_ctas")) { ANCE_REQUIRE(v >= 0, "max_ctas must be >= 0"); ix->max_ctas = v; }
   else { ance::set_error("ance_index_set_param: unknown parameter '%s'", name); return ANCE_ERR_INVALID; }
   return ANCE_OK;
@@ -800,7 +886,8 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // choose k' (candidates kept per split): >= k + 25% margin, multiple of 32
   int kprime = ix->kprime;
-  if (kprime == 0) kprime = std::max(64, ((k + k / 4 + 16) + 31) / 32 * 32);
+  if (kprime == 0) kprime = (k <= 240) ? std::min(512, std::max(64, (2 * k + 32 + 31) / 32 * 32))
+                               : std::min(992, (2 * k + 31) / 32 * 32);
   if (kprime < k || kprime > 992 || k > 512 || ix->n < 4 * static_cast<int64_t>(kprime)) {
     // tiny index or very large k: the exact brute-force path is both correct and cheap enough
     ANCE_REQUIRE(k <= 512, "ance_index_search: k = %d > 512 is not supported", k);
@@ -810,7 +897,6 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
     ix->stats_pending = false;
     return ance_index_search_exact(ix, q_dev, nq, k, D_dev, I_dev, row_offset, stream);
   }
-  const int cap = (kprime <= 512) ? 1024 : 2048;
   // --- 1. quantize queries
   int rc;
   {
@@ -825,79 +911,56 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
   }
   ANCE_CUDA(cudaMemsetAsync(ix->counters, 0, 4 * sizeof(int), st));
   const unsigned qblocks = static_cast<unsigned>((nq + 7) / 8);
+  ance::prof_begin(ance::kClsQuant, st);
   if (ix->fmt == ANCE_FMT_BF16)
     quantize_rows_kernel<true><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, ix->qn_hat, ix->qn_delta, nullptr, ix->err_flag);
   else
     quantize_rows_kernel<false><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, ix->qn_hat, ix->qn_delta, nullptr, ix->err_flag);
+  ance::prof_end(ance::kClsQuant, st);
   ANCE_CUDA(cudaGetLastError());
   ance::count_launch(1);
-  // --- 2. coarse pass
-  const int cg = ix->cta_group;
-  const int clusters = (ix->max_ctas > 0 ? ix->max_ctas : gemm::sm_count()) / cg;
-  const int q_tiles = static_cast<int>((nq + gemm::BM * cg - 1) / (gemm::BM * cg));
-  int n_splits = ix->n_splits;
-  if (n_splits == 0) {
-    // enough work items to fill the machine twice over when there are few query tiles
-    n_splits = (q_tiles >= 2 * clusters) ? 1 : std::min(16, (2 * clusters + q_tiles - 1) / q_tiles);
-    while (n_splits > 1 && n_splits * kprime > 4096) --n_splits;
-  }
-  ANCE_REQUIRE(n_splits * kprime <= 4096, "ance_index_search: n_splits * kprime = %d exceeds 4096", n_splits * kprime);
+  // --- 2+3. tier 1: coarse pass over all queries, exact rescoring, certificate
   int ns = 0;
-  const bool bf = ix->fmt == ANCE_FMT_BF16;
-#define ANCE_COARSE(CG_, CAP_)                                                                            \
-  rc = bf ? launch_coarse<256, (CG_ == 1 ? 4 : 6), CG_, CAP_, tc05::kFmtBF16>(ix, nq, kprime, n_splits, &ns, st) \
-          : launch_coarse<256, (CG_ == 1 ? 4 : 6), CG_, CAP_, tc05::kFmtF16>(ix, nq, kprime, n_splits, &ns, st)
-  if (cg == 1 && cap == 1024) { ANCE_COARSE(1, 1024); }
-  else if (cg == 1) { ANCE_COARSE(1, 2048); }
-  else if (cap == 1024) { ANCE_COARSE(2, 1024); }
-  else { ANCE_COARSE(2, 2048); }
-#undef ANCE_COARSE
+  rc = coarse_rescore_pass(ix, ix->Q16, q_dev, nq, nullptr, kprime, ix->n_splits, k, D_dev, I_dev, row_offset,
+                           ix->flagged, 0, &ns, st);
   if (rc) return rc;
-  // --- 3. exact rescoring + certificate
-  RescoreParams rp;
-  rp.Q = q_dev;
-  rp.P = ix->P32;
-  rp.d = ix->dim;
-  rp.cand_id = ix->cand_id;
-  rp.cand_cnt = ix->cand_cnt;
-  rp.cand_thr = ix->cand_thr;
-  rp.n_splits = ns;
-  rp.kprime = kprime;
-  rp.k = k;
-  rp.qn_hat = ix->qn_hat;
-  rp.qn_delta = ix->qn_delta;
-  rp.pstats = ix->pstats;
-  rp.accum_rel = 3.0517578125e-5f;  // 2^-15, see DESIGN.md "certificate"
-  rp.D = D_dev;
-  rp.I = I_dev;
-  rp.row_offset = row_offset;
-  rp.flagged_list = ix->flagged;
-  rp.counters = ix->counters;
-  rp.max_eps = reinterpret_cast<unsigned int*>(ix->counters + 2);
-  rp.sort_n = next_pow2(ns * kprime);
-  const size_t rs_smem = static_cast<size_t>(rp.sort_n) * 8 + static_cast<size_t>(ix->dim) * 4 + (ns + 1) * 4 + 16;
-  static size_t rs_attr = 0;
-  if (rs_smem > 48 * 1024 && rs_smem > rs_attr) {
-    ANCE_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem)));
-    rs_attr = rs_smem;
-  }
-  rescore_kernel<<<static_cast<unsigned>(nq), 256, rs_smem, st>>>(rp);
-  ANCE_CUDA(cudaGetLastError());
-  ance::count_launch(1);
-  // --- 4. exact fallback for the uncertified queries.  One small D2H + sync per search tells the host
-  // how many there are (the reference's search call is synchronous as well).
+  // One small D2H + sync per search tells the host how many queries stay uncertified (the reference's
+  // search call is synchronous as well).
   int h[4] = {0, 0, 0, 0};
   ANCE_CUDA(cudaMemcpyAsync(h, ix->counters, sizeof(h), cudaMemcpyDeviceToHost, st));
   ANCE_CUDA(cudaStreamSynchronize(st));
-  if (h[0] > 0) {
-    rc = run_exact(ix, q_dev, ix->flagged, h[0], k, D_dev, I_dev, row_offset, st);
+  int n_exact = h[0];
+  int ns2 = 0;
+  const int kprime2 = 992;
+  if (h[0] > 0 && ix->tier2 && kprime < kprime2 && ix->n >= 4 * static_cast<int64_t>(kprime2)) {
+    // --- tier 2: the uncertified queries again with the widest reservoir (k' = 992)
+    const int n2 = h[0];
+    if ((rc = ensure(&ix->Q16b, &ix->q16b_elems, static_cast<size_t>(n2) * ix->dim))) return rc;
+    if ((rc = ensure(&ix->flagged2, &ix->flagged2_cap, static_cast<size_t>(n2)))) return rc;
+    gather_rows16_kernel<<<n2, 96, 0, st>>>(ix->Q16, ix->flagged, n2, ix->dim, ix->Q16b);
+    ANCE_CUDA(cudaGetLastError());
+    ance::count_launch(1);
+    rc = coarse_rescore_pass(ix, ix->Q16b, q_dev, n2, ix->flagged, kprime2, 0, k, D_dev, I_dev, row_offset,
+                             ix->flagged2, 3, &ns2, st);
+    if (rc) return rc;
+    ANCE_CUDA(cudaMemcpyAsync(h, ix->counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+    ANCE_CUDA(cudaStreamSynchronize(st));
+    n_exact = h[3];
+    if (n_exact > 0 && ix->exact_fallback) {
+      rc = run_exact(ix, q_dev, ix->flagged2, n_exact, k, D_dev, I_dev, row_offset, st);
+      if (rc) return rc;
+    }
+  } else if (n_exact > 0 && ix->exact_fallback) {
+    // --- tier 3: exact brute force
+    rc = run_exact(ix, q_dev, ix->flagged, n_exact, k, D_dev, I_dev, row_offset, st);
     if (rc) return rc;
   }
   ix->stats = ance_search_stats{};
   ix->stats.nq = nq;
   ix->stats.kprime = kprime;
   ix->stats.n_splits = ns;
-  ix->stats.n_uncertified = h[0];
+  ix->stats.n_tier2 = h[0];
+  ix->stats.n_uncertified = n_exact;
   ix->stats.n_candidates = h[1];
   memcpy(&ix->stats.max_eps, &h[2], 4);
   ix->last_stream = st;

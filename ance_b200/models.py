@@ -126,7 +126,7 @@ class _CudaEncoder:
             lin, norm = head
             w.head_w, w.head_b = fp(lin.weight), fp(lin.bias)
             w.head_ln_g, w.head_ln_b = fp(norm.weight), fp(norm.bias)
-        self.hidden = H
+        self.hidden_size = H
         self.max_tokens = int(max_tokens)
         h = C.c_void_p()
         with torch.cuda.device(device):
@@ -147,7 +147,7 @@ class _CudaEncoder:
 
     def hidden(self, layer: int, n_tokens: int) -> torch.Tensor:
         """Hidden states after `layer` (0 = embeddings) of the last forward, fp32 [n_tokens, H]."""
-        buf = torch.empty((min(self.max_tokens, 4096), self.hidden), dtype=torch.float32, device=self.device)
+        buf = torch.empty((min(self.max_tokens, 4096), self.hidden_size), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ance_encoder_debug_hidden(self.h, layer, buf.data_ptr(), _lib.current_stream()))
         return buf[:n_tokens]
@@ -155,7 +155,7 @@ class _CudaEncoder:
     def forward(self, ids: torch.Tensor, lens: Optional[torch.Tensor], mask: Optional[torch.Tensor]) -> torch.Tensor:
         """ids int32 [B, L] CUDA; exactly one of lens int32 [B] / mask uint8 [B, L].  -> fp32 [B, H]."""
         B, L = ids.shape
-        out = torch.empty((B, self.hidden), dtype=torch.float32, device=ids.device)
+        out = torch.empty((B, self.hidden_size), dtype=torch.float32, device=ids.device)
         per = max(1, min(self.max_tokens // L, self.max_tokens // 16))
         with torch.cuda.device(ids.device):
             st = _lib.current_stream()

@@ -159,3 +159,9 @@ def merge_topk_host(Ds, Is, k: int, n_threads: int = 0):
     ip = (C.c_void_p * n)(*[i.ctypes.data for i in Is])
     _lib.check(lib.ance_merge_topk_host(dp, ip, n, nq, k, Do.ctypes.data, Io.ctypes.data, n_threads))
     return Do, Io
+
+
+def omp_set_num_threads(n: int) -> None:
+    """faiss.omp_set_num_threads (run_ann_data_gen.py:269): meaningless on the GPU, kept so that
+    ``from ance_b200 import search as faiss`` is a drop-in for the reference's call sites."""
+    return None

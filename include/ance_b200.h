@@ -49,7 +49,8 @@ typedef struct ance_index* ance_index_t;
 
 typedef struct {
   int64_t nq;             /* queries in the last search */
-  int64_t n_uncertified;  /* queries whose coarse pass could not be proven exact -> exact fallback */
+  int64_t n_tier2;        /* queries the first coarse pass could not certify -> second pass with k' = 992 */
+  int64_t n_uncertified;  /* queries no coarse pass could certify -> exact brute-force fallback */
   int64_t n_candidates;   /* candidates rescored in fp32/fp64 */
   int32_t kprime;         /* candidates kept per (query, split) by the coarse pass */
   int32_t n_splits;       /* row-range splits of the corpus per query tile */
@@ -70,8 +71,9 @@ int ance_index_search_exact(ance_index_t idx, const float* q_dev, int64_t nq, in
                             int64_t* I_dev, int64_t row_offset, void* stream);
 /* Blocks on the stream of the last search and returns its statistics. */
 int ance_index_last_stats(ance_index_t idx, ance_search_stats* out);
-/* Tunables: "kprime" (0 = auto), "n_splits" (0 = auto), "cta_group" (1|2), "max_ctas" (0 = all SMs),
- * "coarse_only_timing" (debug). */
+/* Tunables: "kprime" (0 = auto: about 2k), "n_splits" (0 = auto), "cta_group" (1|2), "max_ctas" (0 = all
+ * SMs), "tier2" (0|1), "exact_fallback" (0|1: measurement only — results of uncertified queries are then
+ * NOT guaranteed). */
 int ance_index_set_param(ance_index_t idx, const char* name, double value);
 
 /* Host k-way merge of per-shard results — replaces utils/util.py:87-146 barrier_array_merge +
@@ -125,6 +127,16 @@ int ance_encoder_forward(ance_encoder_t enc, const int32_t* ids_dev, const int32
 /* Debug / parity: copy the hidden states after layer `layer` (0 = embeddings) of the last forward
  * into out_dev [B*L, hidden] fp32. */
 int ance_encoder_debug_hidden(ance_encoder_t enc, int layer, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-time profile by kernel class (bench.py's roofline numbers): CUDA events recorded around every
+ * launch on the launch stream.  Classes: 0 encoder GEMM, 1 attention, 2 LayerNorm/embedding/gather,
+ * 3 operand quantisation, 4 coarse search GEMM, 5 exact rescore, 6 exact brute force.
+ * ance_profile_read synchronises the device, returns milliseconds and launch counts per class
+ * (arrays of length n <= 8) and optionally resets the accumulators.
+ * ------------------------------------------------------------------------------------------------ */
+int ance_profile_enable(int on);
+int ance_profile_read(double* ms_by_class, int64_t* launches_by_class, int n, int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * Bring-up / test hooks (not part of the drop-in surface)

@@ -1,0 +1,180 @@
+"""Parity of the sm_100a flat inner-product search with the CPU oracle (bit-exact: int64 labels and
+fp32 scores), through the C ABI (ance_b200.search.IndexFlatIP -> ctypes -> libance_b200.so)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flat_ip_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _ln_rows(rng, n, d, clustered=True):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    if clustered:
+        cent = np.random.default_rng(7).standard_normal((64, d)).astype(np.float32)
+        x = 0.5 * x + 0.5 * cent[rng.integers(0, 64, size=n)]
+    x = (x - x.mean(1, keepdims=True)) / x.std(1, keepdims=True)
+    return np.ascontiguousarray(x.astype(np.float32))
+
+
+def _index(P, operand="bf16", **params):
+    from ance_b200.search import IndexFlatIP
+    idx = IndexFlatIP(P.shape[1], capacity=max(1, P.shape[0]), operand=operand)
+    idx.add(P)
+    for k, v in params.items():
+        idx.set_param(k, v)
+    return idx
+
+
+def test_golden_kat(golden_dir):
+    g = np.load(os.path.join(golden_dir, "search_kat.npz"))
+    rng = np.random.default_rng(int(g["seed"]))
+    P = rng.standard_normal((3000, 64)).astype(np.float32)
+    P[1500:1510] = P[10:20]
+    Q = rng.standard_normal((16, 64)).astype(np.float32)
+    Q[0] = P[12] * 2
+    for operand in ("bf16", "fp16"):
+        D, I = _index(P, operand).search(Q, 20)
+        assert (I == g["I"]).all() and (D == g["D"]).all()
+
+
+@pytest.mark.parametrize("operand", ["bf16", "fp16"])
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("k", [10, 100, 200])
+def test_seeded_parity(operand, cta_group, k):
+    rng = np.random.default_rng(1234)
+    P = _ln_rows(rng, 60000, 768)
+    Q = _ln_rows(np.random.default_rng(4321), 300, 768)
+    idx = _index(P, operand, cta_group=cta_group)
+    D, I = idx.search(Q, k)
+    Do, Io = flat_ip_oracle.search(P, Q, k)
+    assert (I == Io).all(), f"{(I != Io).any(1).sum()} queries differ"
+    assert (D == Do).all()
+    st = idx.stats()
+    assert st["nq"] == 300 and st["kprime"] >= k
+    # scores within 1e-3 relative of a plain fp32 sgemm (the faiss arithmetic), as north_star asks
+    S = Q @ P.T
+    ref = np.take_along_axis(S, I, axis=1)
+    assert np.abs(D - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+def test_duplicates_and_ties_are_ordered_by_row():
+    rng = np.random.default_rng(5)
+    P = _ln_rows(rng, 20000, 768)
+    P[10000:10050] = P[0:50]           # exact duplicates -> exact score ties
+    Q = _ln_rows(np.random.default_rng(6), 64, 768)
+    Q[:50] = P[0:50] + 0.01 * Q[:50]   # queries whose best neighbours are the duplicated rows
+    D, I = _index(P).search(Q, 20)
+    Do, Io = flat_ip_oracle.search(P, Q, 20)
+    assert (I == Io).all() and (D == Do).all()
+    for q in range(50):
+        a, b = np.where(I[q] == q)[0], np.where(I[q] == 10000 + q)[0]
+        assert len(a) == 1 and len(b) == 1 and b[0] == a[0] + 1  # tie: smaller row first
+
+
+def test_uncertified_queries_fall_back_to_exact():
+    """Rows that differ by less than the 16-bit operand rounding cannot be separated by the coarse pass:
+    the certificate must fail and the exact brute-force path must still return the oracle's answer."""
+    rng = np.random.default_rng(8)
+    base = _ln_rows(rng, 1, 768)
+    P = np.repeat(base, 8192, axis=0) + 1e-4 * rng.standard_normal((8192, 768)).astype(np.float32)
+    Q = _ln_rows(np.random.default_rng(9), 32, 768)
+    idx = _index(P)
+    D, I = idx.search(Q, 50)
+    Do, Io = flat_ip_oracle.search_bruteforce(P, Q, 50)
+    assert (I == Io).all() and (D == Do).all()
+    assert idx.stats()["n_uncertified"] > 0
+
+
+def test_edges_empty_small_and_offsets():
+    rng = np.random.default_rng(10)
+    P = _ln_rows(rng, 37, 768, clustered=False)
+    Q = _ln_rows(np.random.default_rng(11), 5, 768, clustered=False)
+    idx = _index(P)
+    D, I = idx.search(Q, 50)  # fewer rows than k: faiss pads with -1 / lowest float
+    Do, Io = flat_ip_oracle.search_bruteforce(P, Q, 50)
+    assert (I == Io).all() and (D == Do).all() and (I[:, 37:] == -1).all()
+    D0, I0 = idx.search(Q[:0], 5)
+    assert D0.shape == (0, 5) and I0.shape == (0, 5)
+    from ance_b200.search import IndexFlatIP
+    empty = IndexFlatIP(768)
+    De, Ie = empty.search(Q, 3)
+    assert (Ie == -1).all()
+    # row_offset (per-shard global numbering) on the tensor-core path
+    P2 = _ln_rows(rng, 5000, 768)
+    idx2 = _index(P2)
+    Dd, Id = idx2.search_device(torch.from_numpy(Q).cuda(), 10, row_offset=123456)
+    _, Io2 = flat_ip_oracle.search(P2, Q, 10)
+    assert (Id.cpu().numpy() == Io2 + 123456).all()
+    with pytest.raises(ValueError):
+        idx2.search(np.zeros((2, 64), dtype=np.float32), 3)
+    with pytest.raises(TypeError):
+        idx2.search(np.zeros((2, 768), dtype=np.float64), 3)
+
+
+def test_exact_path_equals_oracle():
+    rng = np.random.default_rng(12)
+    P = _ln_rows(rng, 30000, 768)
+    Q = _ln_rows(np.random.default_rng(13), 100, 768)
+    idx = _index(P)
+    D, I = idx.search_device(torch.from_numpy(Q).cuda(), 100, exact=True)
+    Do, Io = flat_ip_oracle.search(P, Q, 100)
+    assert (I.cpu().numpy() == Io).all() and (D.cpu().numpy() == Do).all()
+
+
+def test_sharded_equals_global_on_one_gpu():
+    """SURVEY.md §8(e) on one device: 4 row shards (i % 4), per-shard top-k with offsets, host merge."""
+    from ance_b200.search import merge_topk_host
+    rng = np.random.default_rng(14)
+    P = _ln_rows(rng, 40001, 768)
+    Q = _ln_rows(np.random.default_rng(15), 128, 768)
+    W, k = 4, 100
+    order = np.concatenate([np.arange(r, P.shape[0], W) for r in range(W)])
+    Pm = P[order]
+    Dg, Ig = flat_ip_oracle.search(Pm, Q, k)
+    Ds, Is, off = [], [], 0
+    qd = torch.from_numpy(Q).cuda()
+    for r in range(W):
+        n = len(range(r, P.shape[0], W))
+        D, I = _index(Pm[off:off + n]).search_device(qd, k, row_offset=off)
+        Ds.append(D.cpu().numpy())
+        Is.append(I.cpu().numpy())
+        off += n
+    Dm, Im = merge_topk_host(Ds, Is, k)
+    assert (Im == Ig).all() and (Dm == Dg).all()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (8,841,823 x 768): properties that do not need a full-size CPU oracle."""
+    from ance_b200.search import IndexFlatIP
+    dev = torch.device("cuda:0")
+    N, d, nq, k = 8841823, 768, 1024, 200
+    idx = IndexFlatIP(d, capacity=N)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    cent = torch.randn(1024, d, device=dev, generator=g)
+    probe_rows = torch.randint(0, N, (nq,), generator=torch.Generator().manual_seed(3))
+    keep = {}
+    for s in range(0, N, 1 << 20):
+        e = min(N, s + (1 << 20))
+        x = 0.5 * torch.randn(e - s, d, device=dev, generator=g) + 0.5 * cent[torch.randint(0, 1024, (e - s,), device=dev, generator=g)]
+        x = (x - x.mean(1, keepdim=True)) / x.std(1, keepdim=True, unbiased=False)
+        idx.add(x)
+        m = (probe_rows >= s) & (probe_rows < e)
+        for qi in torch.nonzero(m).flatten().tolist():
+            keep[qi] = x[probe_rows[qi] - s].clone()
+    assert idx.ntotal == N
+    Q = torch.stack([keep[i] for i in range(nq)]) * 1.5  # query i is a scaled copy of row probe_rows[i]
+    D, I = idx.search_device(Q.contiguous(), k)
+    torch.cuda.synchronize()
+    # (1) the planted row is the top hit (Cauchy-Schwarz: all rows have the same norm)
+    assert (I[:, 0].cpu() == probe_rows).all()
+    # (2) sorted descending, labels in range and unique per query
+    assert (D[:, 1:] <= D[:, :-1]).all() and (I >= 0).all() and (I < N).all()
+    assert all(len(set(r)) == k for r in I[:64].cpu().tolist())
+    # (3) identical to the exact brute-force kernel on a slice of the queries
+    De, Ie = idx.search_device(Q[:32].contiguous(), k, exact=True)
+    assert (I[:32] == Ie).all() and (D[:32] == De).all()
+    assert idx.stats()["nq"] == nq
