@@ -124,7 +124,8 @@ def current_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-PROFILE_CLASSES = ("encoder_gemm", "attention", "norm_embed", "quantize", "coarse_search", "rescore", "exact")
+PROFILE_CLASSES = ("gemm_head", "attention", "norm_embed", "quantize", "coarse_search", "rescore", "exact",
+                   "gemm_qkv", "gemm_out", "gemm_ffn1", "gemm_ffn2")
 
 
 def profile_enable(on: bool = True) -> None:
@@ -137,4 +138,7 @@ def profile_read(reset: bool = True) -> dict:
     ms = (C.c_double * n)()
     cnt = (C.c_int64 * n)()
     check(load().ance_profile_read(ms, cnt, n, 1 if reset else 0))
-    return {PROFILE_CLASSES[i]: (ms[i], cnt[i]) for i in range(n)}
+    out = {PROFILE_CLASSES[i]: (ms[i], cnt[i]) for i in range(n)}
+    g = [out[k] for k in ("gemm_head", "gemm_qkv", "gemm_out", "gemm_ffn1", "gemm_ffn2")]
+    out["encoder_gemm"] = (sum(x[0] for x in g), sum(x[1] for x in g))
+    return out

@@ -37,9 +37,10 @@ struct Params {
 
 struct Smem {
   static constexpr int kQ = 0;
-  static constexpr int kK = kQ + kTile * kDh * 2;            // 2 stages
-  static constexpr int kV = kK + 2 * kTile * kDh * 2;        // 2 stages
-  static constexpr int kP = kV + 2 * kTile * kDh * 2;        // 128 x 128 bf16 (two 64-key halves)
+  static constexpr int kStages = 1;                            // K/V stages (1 keeps two CTAs resident per SM)
+  static constexpr int kK = kQ + kTile * kDh * 2;
+  static constexpr int kV = kK + kStages * kTile * kDh * 2;
+  static constexpr int kP = kV + kStages * kTile * kDh * 2;    // 128 x 128 bf16 (two 64-key halves)
   static constexpr int kBias = kP + kTile * kTile * 2;       // 128 floats
   static constexpr int kBar = kBias + kTile * 4;
   // q_full q_empty kv_full[2] kv_empty[2] s p o  + tmem ptr
@@ -47,7 +48,8 @@ struct Smem {
   static constexpr int kDynamic = kTotal + 1024;
 };
 
-__global__ void __launch_bounds__(256, 1)
+template <bool kPacked>  // kPacked: L < 128, a tile holds 128/L sequences
+__global__ void __launch_bounds__(256, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,7 +73,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < Smem::kStages; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
@@ -91,7 +93,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      Ring<2> kv;
+      Ring<Smem::kStages> kv;
       uint32_t wk = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wk) {
         const int tile = w / p.heads, h = w - tile * p.heads;
@@ -116,7 +118,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_f16(kTile, kTile, kFmtBF16, 0, 0);  // Q K^T : both K-major
       constexpr uint32_t idesc_o = make_idesc_f16(kTile, kDh, kFmtBF16, 0, 1);    // P V   : V is MN-major
-      Ring<2> kv;
+      Ring<Smem::kStages> kv;
       uint32_t wk = 0, it = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wk) {
         mbar_wait(q_full, wk & 1, 12);
@@ -187,7 +189,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
           for (int i = 0; i < 32; ++i) {
             const int key = c + i;
             float t = fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[key]);
-            if (key < seq_lo || key >= seq_hi) t = -INFINITY;
+            if (kPacked && (key < seq_lo || key >= seq_hi)) t = -INFINITY;
             m_blk = fmaxf(m_blk, t);
           }
         }
@@ -205,11 +207,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
           for (int i = 0; i < 32; i += 2) {
             float t0 = fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[c + i]);
             float t1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, sbias[c + i + 1]);
-            if (c + i < seq_lo || c + i >= seq_hi) t0 = -INFINITY;
-            if (c + i + 1 < seq_lo || c + i + 1 >= seq_hi) t1 = -INFINITY;
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(exp2f(t0 - m_new), exp2f(t1 - m_new));
-            const float2 back = __bfloat1622float2(h2);
-            rsum += back.x + back.y;
+            if (kPacked && (c + i < seq_lo || c + i >= seq_hi)) t0 = -INFINITY;
+            if (kPacked && (c + i + 1 < seq_lo || c + i + 1 >= seq_hi)) t1 = -INFINITY;
+            const float p0 = exp2f(t0 - m_new), p1 = exp2f(t1 - m_new);
+            rsum += p0 + p1;
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
           }
           // four 16-byte chunks (8 keys each); swizzle: chunk index ^= (row & 7) inside the 128-byte span

@@ -84,7 +84,7 @@ namespace {
 template <int BN, int STAGES, int CG, uint32_t FMT>
 int run_dbg(const void* A, const void* B, int M, int N, int K, const float* bias, const void* R, int act, void* C,
             float* C32, cudaStream_t st) {
-  constexpr int EW = 8;
+  constexpr int EW = (BN >= 128) ? 8 : 4;
   using Ep = gemm::EpStore<BN, EW>;
   CUtensorMap tmA, tmB;
   if (!tc05_host::make_tmap_2d_16b(&tmA, A, M, K, K, gemm::BM) ||
@@ -94,6 +94,11 @@ int run_dbg(const void* A, const void* B, int M, int N, int K, const float* bias
   }
   gemm::WorkShape ws = gemm::make_shape(M, N, K, BN, CG, 0);
   typename Ep::Params p;
+  memset(&p, 0, sizeof(p));
+  if (C && !gemm::make_store_tmap(&p.tmC, C, M, N, N)) {
+    ance::set_error("cuTensorMapEncodeTiled failed for the output (M=%d N=%d)", M, N);
+    return ANCE_ERR_CUDA;
+  }
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.C32 = C32;
   p.bias = bias;

@@ -183,9 +183,13 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const void* __restrict__ i
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int col = (v * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float y[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = (x[v * 8 + i] - mean) * rstd * __ldg(gamma + col + i) + __ldg(beta + col + i);
+    for (int i = 0; i < 8; ++i) y[i] = (x[v * 8 + i] - mean) * rstd * g[i] + bb[i];
     if (out16) {
       uint4 u;
       __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -268,16 +272,21 @@ __nv_bfloat16* upload_bf16(ance_encoder* e, const float* h, size_t n) {
 
 // one GEMM of the forward: C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ R)
 int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, int N, int K, const float* bias,
-           const __nv_bfloat16* R, int act, __nv_bfloat16* C, float* C32, cudaStream_t st) {
-  constexpr int BN = 256, EW = 8;
+           const __nv_bfloat16* R, int act, __nv_bfloat16* C, float* C32, cudaStream_t st, int cls = ance::kClsGemm) {
+  constexpr int BN = 256, EW = 8, CG = 2, STAGES = 6;  // cta_group::2: 256 x 256 tile per CTA pair
   using Ep = gemm::EpStore<BN, EW>;
   CUtensorMap tmA, tmB;
-  if (!tc05_host::make_tmap_2d_16b(&tmA, A, M, K, lda, gemm::BM) || !tc05_host::make_tmap_2d_16b(&tmB, W, N, K, K, BN)) {
+  if (!tc05_host::make_tmap_2d_16b(&tmA, A, M, K, lda, gemm::BM) || !tc05_host::make_tmap_2d_16b(&tmB, W, N, K, K, BN / CG)) {
     ance::set_error("encoder: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", M, N, K);
     return ANCE_ERR_CUDA;
   }
-  gemm::WorkShape ws = gemm::make_shape(M, N, K, BN, 1, 0);
+  gemm::WorkShape ws = gemm::make_shape(M, N, K, BN, CG, 0);
   Ep::Params p;
+  memset(&p, 0, sizeof(p));
+  if (C && !gemm::make_store_tmap(&p.tmC, C, M, N, N)) {
+    ance::set_error("encoder: cuTensorMapEncodeTiled failed for the output (M=%d N=%d)", M, N);
+    return ANCE_ERR_CUDA;
+  }
   p.C = C;
   p.C32 = C32;
   p.bias = bias;
@@ -287,8 +296,8 @@ int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, in
   p.ldr = N;
   p.act = act;
   {
-    ance::ProfScope ps(ance::kClsGemm, st);
-    ANCE_CUDA((gemm::launch<Ep, BN, 4, 1, EW, tc05::kFmtBF16>(tmA, tmB, ws, p, 0, st)));
+    ance::ProfScope ps(cls, st);
+    ANCE_CUDA((gemm::launch<Ep, BN, STAGES, CG, EW, tc05::kFmtBF16>(tmA, tmB, ws, p, 0, st)));
   }
   ance::count_launch(1);
   return ANCE_OK;
@@ -390,7 +399,8 @@ extern "C" int ance_encoder_create(const ance_encoder_config* cfg, const ance_en
   cudaMemset(e->err_flag, 0, sizeof(int));
   static bool attr = false;
   if (!attr) {
-    ANCE_CUDA(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Smem::kDynamic));
+    ANCE_CUDA(cudaFuncSetAttribute(attn::attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Smem::kDynamic));
+    ANCE_CUDA(cudaFuncSetAttribute(attn::attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Smem::kDynamic));
     attr = true;
   }
   *out = e;
@@ -450,19 +460,20 @@ extern "C" int ance_encoder_forward(ance_encoder_t e, const int32_t* ids_dev, co
   ap.kbias = e->kbias; ap.ctx = e->CTX;
   ap.scale_log2 = kLog2e / 8.0f;
   const int attn_work = ((M + 127) / 128) * c.heads;
-  const int attn_grid = std::min(attn_work, gemm::sm_count());
+  const int attn_grid = std::min(attn_work, 2 * gemm::sm_count());
   for (int l = 0; l < c.n_layer; ++l) {
     const LayerDev& d = e->layers[l];
-    if ((rc = linear(e->X, H, M, d.wqkv, 3 * H, H, d.bqkv, nullptr, 0, e->QKV, nullptr, st))) return rc;
+    if ((rc = linear(e->X, H, M, d.wqkv, 3 * H, H, d.bqkv, nullptr, 0, e->QKV, nullptr, st, ance::kClsGemmQkv))) return rc;
     ance::prof_begin(ance::kClsAttn, st);
-    attn::attention_kernel<<<attn_grid, 256, attn::Smem::kDynamic, st>>>(tmQKV, ap);
+    if (L < attn::kTile) attn::attention_kernel<true><<<attn_grid, 256, attn::Smem::kDynamic, st>>>(tmQKV, ap);
+    else attn::attention_kernel<false><<<attn_grid, 256, attn::Smem::kDynamic, st>>>(tmQKV, ap);
     ance::prof_end(ance::kClsAttn, st);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(1);
-    if ((rc = linear(e->CTX, H, M, d.wo, H, H, d.bo, e->X, 0, e->T, nullptr, st))) return rc;
+    if ((rc = linear(e->CTX, H, M, d.wo, H, H, d.bo, e->X, 0, e->T, nullptr, st, ance::kClsGemmOut))) return rc;
     if ((rc = layer_norm(e->T, false, H, M, H, d.ln1g, d.ln1b, c.ln_eps, e->X1, nullptr, st))) return rc;
-    if ((rc = linear(e->X1, H, M, d.w1, F, H, d.b1, nullptr, 1, e->FF, nullptr, st))) return rc;
-    if ((rc = linear(e->FF, F, M, d.w2, H, F, d.b2, e->X1, 0, e->T, nullptr, st))) return rc;
+    if ((rc = linear(e->X1, H, M, d.w1, F, H, d.b1, nullptr, 1, e->FF, nullptr, st, ance::kClsGemmFfn1))) return rc;
+    if ((rc = linear(e->FF, F, M, d.w2, H, F, d.b2, e->X1, 0, e->T, nullptr, st, ance::kClsGemmFfn2))) return rc;
     if ((rc = layer_norm(e->T, false, H, M, H, d.ln2g, d.ln2b, c.ln_eps, e->X, nullptr, st))) return rc;
     if (e->dbg && M <= e->dbg_tokens)
       ANCE_CUDA(cudaMemcpyAsync(e->dbg + static_cast<size_t>(l + 1) * e->dbg_tokens * H, e->X, static_cast<size_t>(M) * H * 2, cudaMemcpyDeviceToDevice, st));

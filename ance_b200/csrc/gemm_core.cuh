@@ -44,16 +44,18 @@ struct EpiCtx {
   int epi_warp;     // 0 .. EPI_WARPS-1
   int lane;
   int work_seq;     // how many work items this CTA has processed before this one
+  uint8_t* ep_smem; // Ep::kSmemBytes of shared memory owned by the epilogue (1024-B aligned)
 };
 
-template <int BN, int STAGES, int CG>
+template <int BN, int STAGES, int CG, int EP_SMEM = 0>
 struct SmemPlan {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBRows = BN / CG;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = STAGES * kStageBytes;
-  static constexpr int kBarOffset = kRingBytes;
+  static constexpr int kEpOffset = kRingBytes;
+  static constexpr int kBarOffset = kRingBytes + EP_SMEM;
   // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] + tmem ptr
   static constexpr int kBarBytes = (2 * STAGES + 4) * 8 + 16;
   static constexpr int kTotal = kBarOffset + kBarBytes;
@@ -63,10 +65,10 @@ struct SmemPlan {
 template <class Ep, int BN, int STAGES, int CG, int EPI_WARPS, uint32_t FMT>
 __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const WorkShape ws, const typename Ep::Params ep) {
+                 const WorkShape ws, const __grid_constant__ typename Ep::Params ep) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(CG == 1 || CG == 2, "CG");
-  using Plan = SmemPlan<BN, STAGES, CG>;
+  using Plan = SmemPlan<BN, STAGES, CG, Ep::kSmemBytes>;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
@@ -90,7 +92,7 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], CG);  // one arrive per producer CTA (+ tx bytes)
+      mbar_init(&full_bar[s], 1);   // the leader CTA's producer arrives once and expects both CTAs' bytes
       mbar_init(&empty_bar[s], 1);  // one tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
@@ -125,8 +127,10 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d(sa, &tmA, &full_bar[ring.stage], kb * BK, a_row, Ep::kHintA);
               tma_load_2d(sb, &tmB, &full_bar[ring.stage], kb * BK, b_row, Ep::kHintB);
             } else {
+              // Both CTAs' TMA bytes complete on the LEADER's barrier; only the leader arrives on it.  The
+              // peer cannot run a phase ahead: it refills a stage only after the MMA that consumed it
+              // (multicast commit on its own empty barrier).
               if (leader) mbar_arrive_expect_tx(&full_bar[ring.stage], 2 * Plan::kStageBytes);
-              else mbar_arrive_cluster(&full_bar[ring.stage], 0);
               tma_load_2d_2sm(sa, &tmA, &full_bar[ring.stage], kb * BK, a_row, Ep::kHintA);
               tma_load_2d_2sm(sb, &tmB, &full_bar[ring.stage], kb * BK, b_row, Ep::kHintB);
             }
@@ -178,6 +182,7 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     cx.epi_warp = warp - 4;
     cx.lane = lane;
     cx.work_seq = 0;
+    cx.ep_smem = smem + Plan::kEpOffset;
     Ring<2> acc;
     for (int w = cluster_id; w < total_work; w += num_clusters, ++cx.work_seq) {
       cx.m_blk = w / ws.n_splits;
@@ -201,6 +206,7 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       epi.end_work(ep, ws, cx);
     }
+    epi.end_kernel(ep, cx);
   }
 
   tc_fence_before_sync();
@@ -224,7 +230,7 @@ inline int sm_count() {
 template <class Ep, int BN, int STAGES, int CG, int EPI_WARPS, uint32_t FMT>
 cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const WorkShape& ws,
                    const typename Ep::Params& ep, int max_ctas, cudaStream_t stream) {
-  using Plan = SmemPlan<BN, STAGES, CG>;
+  using Plan = SmemPlan<BN, STAGES, CG, Ep::kSmemBytes>;
   auto kern = tc05_gemm_kernel<Ep, BN, STAGES, CG, EPI_WARPS, FMT>;
   static bool configured = false;
   if (!configured) {

@@ -133,6 +133,7 @@ struct EpTopK {
   static constexpr uint64_t kHintA = tc05::kEvictLast;   // query tile: re-read for every corpus tile
   static constexpr uint64_t kHintB = tc05::kEvictFirst;  // corpus rows: streamed once per sweep
   static constexpr int kSlots = CAP / 32;
+  static constexpr int kSmemBytes = 0;
   struct Params {
     float* scratch_sc;  // [gridDim.x * 128 * CAP] reservoir scores
     int* scratch_id;    // [gridDim.x * 128 * CAP] reservoir rows
@@ -240,6 +241,8 @@ struct EpTopK {
       }
     }
   }
+
+  __device__ __forceinline__ void end_kernel(const Params&, const gemm::EpiCtx&) {}
 
   __device__ __forceinline__ void end_work(const Params& p, const gemm::WorkShape& ws, const gemm::EpiCtx& cx) {
     __syncwarp();
@@ -566,7 +569,7 @@ struct ance_index {
   unsigned int* pstats = nullptr;  // [2]
   int* err_flag = nullptr;
   // tunables
-  int kprime = 0, n_splits = 0, cta_group = 1, max_ctas = 0, exact_fallback = 1, tier2 = 1;
+  int kprime = 0, n_splits = 0, cta_group = 2, max_ctas = 0, exact_fallback = 1, tier2 = 1;
   // workspace (grown lazily)
   uint16_t* Q16 = nullptr; float* qn_hat = nullptr; float* qn_delta = nullptr; int64_t q_cap = 0;
   float* scratch_sc = nullptr; int* scratch_id = nullptr; size_t scratch_elems = 0;

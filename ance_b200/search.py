@@ -6,8 +6,9 @@ Mirrors the three calls the reference makes (drivers/run_ann_data_gen.py:269-276
     _, I = cpu_index.search(query_embedding, top_k)
 
 ``IndexFlatIP`` accepts numpy arrays (host, as the reference passes) or CUDA torch tensors (no
-copy).  ``ShardedIndexFlatIP`` is the multi-GPU form of SURVEY.md §8(e): rows stay on the rank that
-encoded them, queries are all-gathered once, per-shard top-k lists are merged on the host.
+copy).  The multi-GPU form of SURVEY.md §8(e) — rows stay on the rank that encoded them, queries are
+all-gathered once, per-shard top-k lists are merged on the host with ``merge_topk_host`` — lives in
+``ance_b200.drivers.run_ann_data_gen.sharded_search``.
 There is no CPU fallback: without libance_b200.so and an sm_100 GPU every call raises.
 """
 from __future__ import annotations

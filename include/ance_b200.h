@@ -131,9 +131,10 @@ int ance_encoder_debug_hidden(ance_encoder_t enc, int layer, float* out_dev, voi
 /* ------------------------------------------------------------------------------------------------
  * Device-time profile by kernel class (bench.py's roofline numbers): CUDA events recorded around every
  * launch on the launch stream.  Classes: 0 encoder GEMM, 1 attention, 2 LayerNorm/embedding/gather,
- * 3 operand quantisation, 4 coarse search GEMM, 5 exact rescore, 6 exact brute force.
+ * 3 operand quantisation, 4 coarse search GEMM, 5 exact rescore, 6 exact brute force, 7-10 encoder
+ * GEMMs by role (QKV, attention out-proj, FFN up, FFN down; class 0 then holds the head GEMM only).
  * ance_profile_read synchronises the device, returns milliseconds and launch counts per class
- * (arrays of length n <= 8) and optionally resets the accumulators.
+ * (arrays of length n <= 12) and optionally resets the accumulators.
  * ------------------------------------------------------------------------------------------------ */
 int ance_profile_enable(int on);
 int ance_profile_read(double* ms_by_class, int64_t* launches_by_class, int n, int reset);

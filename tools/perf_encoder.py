@@ -50,6 +50,7 @@ def main():
                "norm_ms": prof["norm_embed"][0] / it,
                "gemm_tflops": gemm_flop / (prof["encoder_gemm"][0] / it) / 1e9,
                "attn_tflops": attn_flop / (prof["attention"][0] / it) / 1e9,
+               "by_gemm_ms": {k: round(prof[k][0] / it, 4) for k in ("gemm_qkv", "gemm_out", "gemm_ffn1", "gemm_ffn2", "gemm_head")},
                "launches": {k: v[1] // it for k, v in prof.items() if v[1]}}
         print(json.dumps(rec), flush=True)
         out.write(json.dumps(rec) + "\n")
