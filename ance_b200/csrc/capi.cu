@@ -99,6 +99,10 @@ int run_dbg(const void* A, const void* B, int M, int N, int K, const float* bias
     ance::set_error("cuTensorMapEncodeTiled failed for the output (M=%d N=%d)", M, N);
     return ANCE_ERR_CUDA;
   }
+  if (C && R && !gemm::make_store_tmap(&p.tmR, const_cast<void*>(R), M, N, N)) {
+    ance::set_error("cuTensorMapEncodeTiled failed for the residual (M=%d N=%d)", M, N);
+    return ANCE_ERR_CUDA;
+  }
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.C32 = C32;
   p.bias = bias;

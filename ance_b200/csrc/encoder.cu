@@ -287,6 +287,10 @@ int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, in
     ance::set_error("encoder: cuTensorMapEncodeTiled failed for the output (M=%d N=%d)", M, N);
     return ANCE_ERR_CUDA;
   }
+  if (C && R && !gemm::make_store_tmap(&p.tmR, const_cast<__nv_bfloat16*>(R), M, N, N)) {
+    ance::set_error("encoder: cuTensorMapEncodeTiled failed for the residual (M=%d N=%d)", M, N);
+    return ANCE_ERR_CUDA;
+  }
   p.C = C;
   p.C32 = C32;
   p.bias = bias;

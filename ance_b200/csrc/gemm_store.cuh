@@ -26,21 +26,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));   // MUFU.RCP, rel. error 2^-23
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(-1.4426950408889634f * ax * ax);  // MUFU.EX2, rel. error 2^-22
-  return copysignf(fmaf(-p, e, 1.0f), x);
-}
-
+// HF "gelu": x * 0.5 * (1 + erf(x / sqrt(2))), with the 1/sqrt(2) and 0.5 folded into the constants:
+//   t = 1 / (1 + p|x|/sqrt2),  h = 0.5 - (sum a_i/2 t^i) * exp(-x^2/2),  gelu = 0.5 x + |x| h
+// 13 FP32 ops + MUFU.RCP + MUFU.EX2 per element.
 __device__ __forceinline__ float gelu_erf(float x) {
-  // HF "gelu": x * 0.5 * (1 + erf(x / sqrt(2)))
-  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.23164189f, ax, 1.0f));
+  float q = fmaf(0.5307027145f, t, -0.7265760135f);
+  q = fmaf(q, t, 0.7107068705f);
+  q = fmaf(q, t, -0.142248368f);
+  q = fmaf(q, t, 0.127414796f);
+  q *= t;
+  const float e = ex2_approx(x * (-0.72134752044f * x));
+  const float h = fmaf(-q, e, 0.5f);
+  return fmaf(ax, h, 0.5f * x);
 }
 
 template <int BN, int EPI_WARPS>
@@ -50,11 +49,12 @@ struct EpStore {
   static constexpr int kColGroups = EPI_WARPS / 4;
   static constexpr int kColsPerGroup = BN / kColGroups;
   static constexpr int kSlabBytes = BM * 128;            // 128 rows x 64 bf16
-  static constexpr int kSmemBytes = kColGroups * kSlabBytes;
+  static constexpr int kSmemBytes = kColGroups * kSlabBytes + 64;  // slabs + one residual mbarrier per column group
   static_assert(EPI_WARPS % 4 == 0 && kColsPerGroup % 64 == 0, "epilogue warp layout");
 
   struct alignas(64) Params {
     CUtensorMap tmC;         // bf16 output [M, N], box {64, 128}, SWIZZLE_128B (valid when C != null)
+    CUtensorMap tmR;         // bf16 residual, same geometry (valid when R != null and C != null)
     __nv_bfloat16* C;        // [M, ldc] bf16 or null
     float* C32;              // [M, ldc32] fp32 or null (direct stores)
     const float* bias;       // [N] or null
@@ -63,7 +63,20 @@ struct EpStore {
     int act;                 // 0 none, 1 gelu(erf)
   };
 
-  __device__ __forceinline__ void begin_work(const Params&, const WorkShape&, const EpiCtx&) {}
+  uint32_t rphase;
+
+  __device__ __forceinline__ void begin_work(const Params& p, const WorkShape&, const EpiCtx& cx) {
+    if (cx.work_seq == 0 && p.R && p.C) {  // residual tiles arrive by TMA: one mbarrier per column group
+      const int cgi = cx.epi_warp >> 2;
+      uint64_t* rbar = reinterpret_cast<uint64_t*>(cx.ep_smem + kColGroups * kSlabBytes) + cgi;
+      if ((cx.epi_warp & 3) == 0 && cx.lane == 0) {
+        tc05::mbar_init(rbar, 1);
+        tc05::fence_barrier_init();
+      }
+      tc05::named_bar_sync(2 + cgi, 128);
+      rphase = 0;
+    }
+  }
   __device__ __forceinline__ void end_work(const Params&, const WorkShape&, const EpiCtx&) {}
   __device__ __forceinline__ void end_kernel(const Params& p, const EpiCtx& cx) {
     if (p.C && (cx.epi_warp & 3) == 0 && cx.lane == 0) tc05::bulk_wait_all();
@@ -71,7 +84,7 @@ struct EpStore {
 
   // bias + activation + residual on one 32-column chunk held as fp32
   __device__ __forceinline__ void finish_chunk(const Params& p, const WorkShape& ws, float (&f)[32], int row,
-                                               bool row_ok, int col0) {
+                                               bool row_ok, int col0, bool direct_residual) {
     const bool full = (col0 + 32 <= ws.N);
     if (p.bias) {
       if (full) {
@@ -90,7 +103,7 @@ struct EpStore {
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
     }
-    if (p.R && row_ok) {
+    if (direct_residual && p.R && row_ok) {
       const __nv_bfloat16* r = p.R + (size_t)row * p.ldr + col0;
       if (full) {
 #pragma unroll
@@ -124,16 +137,31 @@ struct EpStore {
       const int col_in_tile = cgi * kColsPerGroup + s;
       const int col0 = nb * BN + col_in_tile;
       if (col0 >= ws.N) break;  // uniform across the column group
-      uint32_t pk[32];
+      const bool tma_res = (p.R != nullptr) && (p.C != nullptr);
+      uint64_t* rbar = reinterpret_cast<uint64_t*>(cx.ep_smem + kColGroups * kSlabBytes) + cgi;
+      uint8_t* rowp = slab + r_in_tile * 128;
+      if (tma_res && issuer) {
+        // residual slab -> the staging buffer (free once the previous TMA store has read it)
+        tc05::bulk_wait_read_all();
+        tc05::mbar_arrive_expect_tx(rbar, kSlabBytes);
+        tc05::tma_load_2d(slab, &p.tmR, rbar, col0, cx.row0, tc05::kEvictFirst);
+      }
+      // both 32-column halves of the slab are requested from TMEM before the first is consumed
+      uint32_t va[32], vb[32];
+      tc05::tmem_ld_32x32b_x32(tacc + col_in_tile, va);
+      tc05::tmem_ld_32x32b_x32(tacc + col_in_tile + 32, vb);
+      tc05::tmem_ld_wait();
+      if (!tma_res && p.C) {
+        // the slab is free once the previous TMA store has finished reading it
+        if (issuer) tc05::bulk_wait_read_all();
+        tc05::named_bar_sync(2 + cgi, 128);
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tc05::tmem_ld_32x32b_x32(tacc + col_in_tile + h * 32, v);
-        tc05::tmem_ld_wait();
         float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        finish_chunk(p, ws, f, row, row_ok, col0 + h * 32);
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(h == 0 ? va[i] : vb[i]);
+        finish_chunk(p, ws, f, row, row_ok, col0 + h * 32, !tma_res);
         if (p.C32 && row_ok) {
           float* o = p.C32 + (size_t)row * p.ldc32 + col0 + h * 32;
           if (col0 + h * 32 + 32 <= ws.N) {
@@ -145,21 +173,31 @@ struct EpStore {
               if (col0 + h * 32 + i < ws.N) o[i] = f[i];
           }
         }
+        if (p.C) {
+          if (tma_res && h == 0) tc05::mbar_wait(rbar, rphase, 20);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-          pk[h * 16 + i] = *reinterpret_cast<const uint32_t*>(&h2);
+          for (int q = 0; q < 4; ++q) {  // 16-byte chunk (h*4 + q) of this row, 128-byte swizzle
+            uint4* cp = reinterpret_cast<uint4*>(rowp + (((h * 4 + q) ^ (r_in_tile & 7)) * 16));
+            if (tma_res) {
+              const uint4 rv = *cp;
+              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 x = __bfloat1622float2(rh[t]);
+                f[q * 8 + t * 2] += x.x;
+                f[q * 8 + t * 2 + 1] += x.y;
+              }
+            }
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) oh[t] = __floats2bfloat162_rn(f[q * 8 + t * 2], f[q * 8 + t * 2 + 1]);
+            *cp = o;
+          }
         }
       }
       if (p.C) {
-        // the slab is free once the previous TMA store has finished reading it
-        if (issuer) tc05::bulk_wait_read_all();
-        tc05::named_bar_sync(2 + cgi, 128);
-        uint8_t* rowp = slab + r_in_tile * 128;
-#pragma unroll
-        for (int q = 0; q < 8; ++q)  // 16-byte chunk q of this row, 128-byte swizzle
-          *reinterpret_cast<uint4*>(rowp + ((q ^ (r_in_tile & 7)) * 16)) =
-              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        if (tma_res) rphase ^= 1;
         tc05::fence_proxy_async_smem();
         tc05::named_bar_sync(2 + cgi, 128);
         if (issuer) {

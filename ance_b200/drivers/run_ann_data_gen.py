@@ -143,10 +143,11 @@ def rows_from_batches(emb: torch.Tensor, idx: np.ndarray, batch: int) -> Tuple[t
 class B200Backend:
     """Encode + search on this rank's GPU through libance_b200."""
 
-    def __init__(self, args, model):
+    def __init__(self, args, model, mask_mode: str = "lens"):
         self.args = args
         self.model = model
         self.device = args.device
+        self.mask_mode = mask_mode  # "lens": 1^len 0^(L-len) (msmarco_data.py:282); "nonzero": ids != 0 (DPR_data.py:283)
 
     def encode(self, cache_path: str, is_query: bool) -> Tuple[torch.Tensor, np.ndarray]:
         """This rank's records of one token cache -> (rows [n_rows, 768] fp32 CUDA, embedding2id int64)."""
@@ -164,7 +165,10 @@ class B200Backend:
             for ids, lens, idx in reader:
                 ids_d = ids.to(self.device, non_blocking=True)
                 lens_d = lens.to(self.device, non_blocking=True)
-                if multi:
+                if self.mask_mode == "nonzero":
+                    fn = self.model.query_emb if is_query else self.model.body_emb
+                    e, i = fn(ids_d, ids_d != 0), idx.numpy()
+                elif multi:
                     e = self.model.encode_lens_multi_chunk(ids_d, lens_d)
                     e, i = rows_from_batches(e, idx.numpy(), B)
                 else:

@@ -128,6 +128,12 @@ def cpu_step_sample(threads, n_p=32, n_q=16, search_q=64, search_rows=262144):
     return rate_p, rate_q, qps_full, time.time() - t_all
 
 
+def cpu_threads():
+    """The reference pins its CPU search to 16 OpenMP threads (run_ann_data_gen.py:269); small-batch fp32
+    matmuls stop scaling (and regress) far below the 128+ hardware threads of a B200 host."""
+    return min(os.cpu_count() or 1, 16)
+
+
 def cpu_value(pb, qb, rate_p, rate_q, qps_full):
     t = pb / rate_p + qb / rate_q + qb / qps_full
     return (pb + qb) / t
@@ -137,7 +143,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     pb, qb = args.passages_per_step, args.queries_per_step
     vals, spent = [], 0.0
     for i in range(args.warmup + args.steps):
@@ -337,13 +343,14 @@ def run_b200(args):
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        rate_p, rate_q, qps, dt = cpu_step_sample(threads)
+        threads = cpu_threads()
+        rate_p, rate_q, qps, dt = cpu_step_sample(threads, n_p=16, n_q=8, search_q=32, search_rows=131072)
         out["cpu_baseline"] = {
             "value": cpu_value(pb, qb, rate_p, rate_q, qps), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "32 passages L=128 + 16 queries L=64 through the oracle port of the reference's HF-RoBERTa eager fp32 "
-                      "path (batch 16); 64 queries x 262,144 rows blocked fp32 sgemm + top-200 (faiss IndexFlatIP "
-                      "arithmetic), scaled linearly to N=8,841,823; %.0f s of CPU work" % dt,
+            "sample": "16 passages L=128 + 8 queries L=64 through the oracle port of the reference's HF-RoBERTa eager fp32 "
+                      "path (batch 16); 32 queries x 131,072 rows blocked fp32 sgemm + top-200 (faiss IndexFlatIP "
+                      "arithmetic), scaled linearly to N=8,841,823; %d threads (the reference pins faiss to 16, "
+                      "run_ann_data_gen.py:269); %.0f s of CPU work" % (threads, dt),
             "passages_per_s": rate_p, "queries_top200_per_s": qps}
     print(json.dumps(out))
 

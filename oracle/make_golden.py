@@ -288,6 +288,48 @@ def golden_search():
     np.savez_compressed(os.path.join(GOLD, "search_kat.npz"), seed=3, D=D, I=I)
 
 
+def golden_dpr():
+    """utils/dpr_utils.py has_answer + the DPR driver's validate / GenerateNegativePassaageID (reference code)."""
+    sys.modules["transformers"].__dict__.setdefault("AdamW", torch.optim.AdamW)
+    from utils.dpr_utils import SimpleTokenizer, has_answer
+    import drivers.run_ann_data_gen_dpr as ddrv
+
+    tok = SimpleTokenizer()
+    texts = [
+        "Paris is the capital and most populous city of France.",
+        "The Eiffel Tower (/ˈaɪfəl/ EYE-fəl) was built in 1889; Gustave Eiffel's company designed it.",
+        "Zürich — Switzerland's largest city — lies at the north-western tip of Lake Zürich.",
+        "In 1969, Apollo 11 landed on the Moon. Neil Armstrong said: 'one small step'.",
+        "",
+        "U.S.A. and u.s.a are tokenised differently from USA",
+        "naïve café déjà vu",
+    ]
+    answers = [["paris"], ["Gustave Eiffel"], ["zurich"], ["Zürich"], ["apollo 11", "Apollo 12"], ["one small step"],
+               ["small  step"], ["1969,"], ["u.s.a"], ["USA"], ["cafe"], ["café"], [""], ["the Moon.", "nothing"],
+               ["north-western"], ["EYE-fəl"]]
+    table = [[bool(has_answer(a, t, tok)) for t in texts] for a in answers]
+    rng = np.random.default_rng(4)
+    n_p, n_q, k = 60, 12, 10
+    words = ["alpha", "beta", "gamma", "delta", "omega", "paris", "rome", "1969", "moon", "tower"]
+    passages = {i: (" ".join(rng.choice(words, size=12)), "t%d" % i) for i in range(n_p)}
+    q_answers = [[str(rng.choice(words))] + ([str(rng.choice(words)) + " " + str(rng.choice(words))] if q % 3 == 0 else [])
+                 for q in range(n_q)]
+    p2id = rng.permutation(n_p).astype(np.int64)
+    q2id = rng.permutation(n_q).astype(np.int64)
+    I = np.stack([rng.permutation(n_p)[:k] for _ in range(n_q)])
+    pos = [int(rng.integers(0, n_p)) for _ in range(n_q)]
+    for q in range(0, n_q, 2):
+        pos[int(q2id[q])] = int(p2id[I[q, 1]])  # the positive is among the neighbours of some queries
+    args = argparse.Namespace(negative_sample=4)
+    negs = ddrv.GenerateNegativePassaageID(args, passages, q_answers, q2id, p2id, I, pos)
+    hits = ddrv.validate(passages, q_answers, I, q2id, p2id)
+    with open(os.path.join(GOLD, "dpr_postprocess.json"), "w") as f:
+        json.dump({"texts": texts, "answers": answers, "has_answer": table, "seed": 4, "n_p": n_p, "n_q": n_q, "k": k,
+                   "negatives": {str(k_): [int(x) for x in v] for k_, v in negs.items()}, "top_k_hits": hits,
+                   "negative_sample": 4}, f)
+    print("dpr golden: hit@k", hits[0], hits[-1], "has_answer trues", sum(map(sum, table)))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     stub_third_party()
@@ -296,5 +338,7 @@ if __name__ == "__main__":
     golden_search()
     golden_io()
     golden_postprocess()
-    golden_encoders()
+    golden_dpr()
+    if "--no-encoders" not in sys.argv:
+        golden_encoders()
     print("golden fixtures written to", GOLD)

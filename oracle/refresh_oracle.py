@@ -231,3 +231,61 @@ def latest_ann_data(ann_dir: str):
     with open(os.path.join(ann_dir, prefix + str(no))) as f:
         js = json.load(f)
     return no, os.path.join(ann_dir, "ann_training_data_" + str(no)), js
+
+
+# ---------------------------------------------------------------------------------------------
+# DPR post-processing (drivers/run_ann_data_gen_dpr.py:281-340, utils/dpr_utils.py:241-306)
+# ---------------------------------------------------------------------------------------------
+def dpr_words(text: str) -> List[str]:
+    """SimpleTokenizer().tokenize(NFD(text)).words(uncased=True): utils/dpr_utils.py:253-257,267-306,331-338."""
+    import unicodedata
+
+    import regex
+    pat = regex.compile(r"([\p{L}\p{N}\p{M}]+)|([^\p{Z}\p{C}])", flags=regex.IGNORECASE + regex.UNICODE + regex.MULTILINE)
+    return [m.group().lower() for m in pat.finditer(unicodedata.normalize("NFD", text))]
+
+
+def dpr_has_answer(answers: Sequence[str], text) -> bool:
+    """utils/dpr_utils.py:241-264."""
+    if text is None:
+        return False
+    words = dpr_words(text)
+    for a in answers:
+        aw = dpr_words(a)
+        for i in range(0, len(words) - len(aw) + 1):
+            if aw == words[i:i + len(aw)]:
+                return True
+    return False
+
+
+def dpr_generate_negatives(passages, answers, query_embedding2id, passage_embedding2id, I, positives, negative_sample):
+    """run_ann_data_gen_dpr.py:281-309: rank order, answer filter, neg_cnt advances on rejected candidates too."""
+    out = {}
+    for qi in range(I.shape[0]):
+        qid = int(query_embedding2id[qi])
+        negs, cnt = [], 0
+        for pidx in I[qi]:
+            doc = int(passage_embedding2id[pidx])
+            if doc == positives[qid] or doc in negs:
+                continue
+            if cnt >= negative_sample:
+                break
+            if not dpr_has_answer(answers[qid], passages[doc][0]):
+                negs.append(doc)
+            cnt += 1
+        out[qid] = negs
+    return out
+
+
+def dpr_validate(passages, answers, I, query_embedding2id, passage_embedding2id) -> List[float]:
+    """run_ann_data_gen_dpr.py:312-340: hit@k for k = 1..n_docs."""
+    n_docs = I.shape[1]
+    hits = [0] * n_docs
+    for qi in range(I.shape[0]):
+        qid = int(query_embedding2id[qi])
+        flags = [dpr_has_answer(answers[qid], passages[int(passage_embedding2id[p])][0]) for p in I[qi]]
+        best = next((i for i, x in enumerate(flags) if x), None)
+        if best is not None:
+            for j in range(best, n_docs):
+                hits[j] += 1
+    return [v / I.shape[0] for v in hits]
