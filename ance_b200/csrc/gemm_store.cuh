@@ -66,7 +66,7 @@ struct EpStore {
   uint32_t rphase;
 
   __device__ __forceinline__ void begin_work(const Params& p, const WorkShape&, const EpiCtx& cx) {
-    if (cx.work_seq == 0 && p.R && p.C) {  // residual tiles arrive by TMA: one mbarrier per column group
+    if (cx.work_seq == 0 && p.R && p.C && !p.C32) {  // residual tiles arrive by TMA: one mbarrier per column group
       const int cgi = cx.epi_warp >> 2;
       uint64_t* rbar = reinterpret_cast<uint64_t*>(cx.ep_smem + kColGroups * kSlabBytes) + cgi;
       if ((cx.epi_warp & 3) == 0 && cx.lane == 0) {
@@ -137,7 +137,7 @@ struct EpStore {
       const int col_in_tile = cgi * kColsPerGroup + s;
       const int col0 = nb * BN + col_in_tile;
       if (col0 >= ws.N) break;  // uniform across the column group
-      const bool tma_res = (p.R != nullptr) && (p.C != nullptr);
+      const bool tma_res = (p.R != nullptr) && (p.C != nullptr) && (p.C32 == nullptr);
       uint64_t* rbar = reinterpret_cast<uint64_t*>(cx.ep_smem + kColGroups * kSlabBytes) + cgi;
       uint8_t* rowp = slab + r_in_tile * 128;
       if (tma_res && issuer) {

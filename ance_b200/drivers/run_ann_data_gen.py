@@ -171,6 +171,8 @@ class B200Backend:
                 elif multi:
                     e = self.model.encode_lens_multi_chunk(ids_d, lens_d)
                     e, i = rows_from_batches(e, idx.numpy(), B)
+                elif getattr(args, "length_buckets", True):
+                    e, i = self.model.encode_lens_bucketed(ids_d, lens_d), idx.numpy()
                 else:
                     e, i = self.model.encode_lens(ids_d, lens_d), idx.numpy()
                 outs.append(e)
@@ -350,6 +352,9 @@ def get_arguments(argv=None):
                    help="draw the negative-sampling order from Python's `random` exactly as the reference does")
     p.add_argument("--seed", default=None, type=int, help="seed for the sampling order (reference: unseeded)")
     p.add_argument("--poll_seconds", default=60, type=int)
+    p.add_argument("--no_length_buckets", dest="length_buckets", action="store_false",
+                   help="encode every sequence at the cache's full padded length (the reference's behaviour); by default "
+                        "sequences are grouped by the smallest supported padded length, which yields the same embeddings")
     return p.parse_args(argv)
 
 

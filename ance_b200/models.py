@@ -266,6 +266,25 @@ class RobertaDot_NLL_LN(_B200Encoder):
     def encode_lens(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor) -> torch.Tensor:
         return self._encoder(ids_i32.device).forward(ids_i32.contiguous(), lens_i32.contiguous(), None)
 
+    def encode_lens_bucketed(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor, min_bucket: int = 16) -> torch.Tensor:
+        """Same result as encode_lens, without the FLOPs of all-padding tails: sequences are grouped by the
+        smallest supported padded length >= their own length (16/32/64/128/256/384/512) and each group is
+        encoded at that length.  Padding keys carry the additive -10000 (probability exactly 0 in fp32) and
+        padding rows are never read, so dropping trailing pad columns does not change a sequence's embedding."""
+        B, L = ids_i32.shape
+        buckets = [b for b in (8, 16, 32, 64) if min_bucket <= b < L] + [b for b in range(128, L + 1, 128)]
+        if not buckets or buckets[-1] != L:
+            buckets.append(L)
+        bt = torch.tensor(buckets, device=lens_i32.device, dtype=torch.int32)
+        which = torch.bucketize(lens_i32.clamp(min=1), bt)  # first bucket with capacity >= len
+        out = torch.empty((B, 768), dtype=torch.float32, device=ids_i32.device)
+        for bi, Lb in enumerate(buckets):
+            sel = torch.nonzero(which == bi).flatten()
+            if sel.numel() == 0:
+                continue
+            out[sel] = self.encode_lens(ids_i32[sel, :Lb].contiguous(), lens_i32[sel].contiguous())
+        return out
+
 
 class RobertaDot_CLF_ANN_NLL_MultiChunk(RobertaDot_NLL_LN):
     """model/models.py:160-199: documents are 4 independent 512-token chunks; one vector per chunk."""
@@ -312,7 +331,11 @@ class BiEncoder(_B200Encoder):
 
     def __init__(self, args=None):
         super().__init__()
-        d = _BertDims
+
+        class d(_BertDims):  # bert-base-uncased unless `args` overrides a dimension (tests use small models)
+            num_hidden_layers = getattr(args, "num_hidden_layers", _BertDims.num_hidden_layers)
+            vocab_size = getattr(args, "vocab_size", _BertDims.vocab_size)
+
         self.dims = d
         self.question_model = _backbone(d.vocab_size, d.hidden_size, d.num_hidden_layers, d.intermediate_size,
                                         d.max_position_embeddings, d.type_vocab_size, d.pad_token_id, d.layer_norm_eps)

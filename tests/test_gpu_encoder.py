@@ -87,6 +87,21 @@ def test_ragged_batch_and_batch_invariance(rdot):
     assert torch.isfinite(all5).all()
 
 
+def test_length_buckets_do_not_change_embeddings(rdot):
+    model, _ = rdot
+    rng = np.random.default_rng(4)
+    lens = torch.tensor([1, 7, 16, 17, 31, 33, 64, 65, 100, 128, 12, 50], dtype=torch.int32, device="cuda")
+    ids = torch.from_numpy(rng.integers(3, 50265, size=(12, 128)).astype(np.int32)).cuda()
+    ids[:, 0] = 0
+    for b in range(12):
+        ids[b, lens[b]:] = 1
+    dense = model.encode_lens(ids, lens)
+    packed = model.encode_lens_bucketed(ids, lens)
+    # same arithmetic per row; only the number of exactly-zero softmax terms differs
+    assert torch.allclose(dense, packed, rtol=0, atol=2e-3)
+    assert torch.nn.functional.cosine_similarity(dense, packed, dim=-1).min().item() > 0.999999
+
+
 def test_multi_chunk_vs_reference_golden(golden_dir):
     from ance_b200.models import RobertaDot_CLF_ANN_NLL_MultiChunk
     sd = random_roberta_state_dict(seed=0)

@@ -41,6 +41,12 @@ def child(variant: int, fmt: int, M: int, N: int, K: int, epi: int):
         ref = torch.nn.functional.gelu(ref + bias) + R.float()
     err = (C32 - ref).abs().max().item()
     err16 = (C16.float() - ref).abs().max().item()
+    if epi:  # bf16-only output with residual: the TMA-residual path of the epilogue
+        C16b = torch.zeros_like(C16)
+        lib.ance_dbg_gemm(A.data_ptr(), B.data_ptr(), M, N, K, fmt, variant, bias.data_ptr(), R.data_ptr(), 1,
+                          C16b.data_ptr(), None, st)
+        torch.cuda.synchronize()
+        err16 = max(err16, (C16b.float() - ref).abs().max().item())
     nan = int(torch.isnan(C32).sum().item())
     # timing
     for _ in range(3):
@@ -55,7 +61,7 @@ def child(variant: int, fmt: int, M: int, N: int, K: int, epi: int):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     tf = 2.0 * M * N * K / ms / 1e9
-    print(json.dumps({"ok": bool(err < 0.05 and nan == 0), "max_err_f32": err, "max_err_bf16": err16, "nan": nan,
+    print(json.dumps({"ok": bool(err < 0.05 and err16 < 0.3 and nan == 0), "max_err_f32": err, "max_err_bf16": err16, "nan": nan,
                       "ms": ms, "tflops": tf}))
 
 
