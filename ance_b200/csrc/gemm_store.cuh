@@ -13,8 +13,6 @@
 
 namespace gemm {
 
-// erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): one MUFU.RCP + one MUFU.EX2 + 7 FMA —
-// three orders of magnitude below the bf16 rounding applied to the result.
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -26,20 +24,51 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 
-// HF "gelu": x * 0.5 * (1 + erf(x / sqrt(2))), with the 1/sqrt(2) and 0.5 folded into the constants:
-//   t = 1 / (1 + p|x|/sqrt2),  h = 0.5 - (sum a_i/2 t^i) * exp(-x^2/2),  gelu = 0.5 x + |x| h
-// 13 FP32 ops + MUFU.RCP + MUFU.EX2 per element.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x);
-  const float t = rcp_approx(fmaf(0.23164189f, ax, 1.0f));
-  float q = fmaf(0.5307027145f, t, -0.7265760135f);
-  q = fmaf(q, t, 0.7107068705f);
-  q = fmaf(q, t, -0.142248368f);
-  q = fmaf(q, t, 0.127414796f);
-  q *= t;
-  const float e = ex2_approx(x * (-0.72134752044f * x));
-  const float h = fmaf(-q, e, 0.5f);
-  return fmaf(ax, h, 0.5f * x);
+// Packed fp32 pairs (Blackwell FFMA2 / fma.rn.f32x2): the FP32 pipe, not the issue rate, bounds the GELU
+// epilogue, and FFMA2 does two elements per slot at full fp32 precision.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// HF "gelu" = x * 0.5 * (1 + erf(x / sqrt(2))) = relu(x) - 0.5 |x| erfc(|x| / sqrt(2)), with
+//   erfc(z) ~= (1 + a1 z + ... + a6 z^6)^-16        (Abramowitz & Stegun 7.1.28, |error| <= 3e-7)
+// and the 1/sqrt(2) folded into the coefficients.  Measured |error| of the GELU <= 7.1e-7 absolute (three
+// orders of magnitude below the bf16 rounding of the output).  The epilogue of the FFN-up GEMM is bound by
+// the SFU (MUFU) rate, so this form uses ONE MUFU (rcp) per element and no exponential; everything else is
+// packed FFMA2/FMUL2: per PAIR of elements 14 packed fp32 ops + 2 LOP + 2 MUFU.RCP.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x = pack2(x0, x1);
+  const uint64_t ax = x & 0x7FFFFFFF7FFFFFFFull;
+  uint64_t p = fma2(pack2(5.38297490e-06f, 5.38297490e-06f), ax, pack2(4.88906371e-05f, 4.88906371e-05f));
+  p = fma2(p, ax, pack2(3.80035744e-05f, 3.80035744e-05f));
+  p = fma2(p, ax, pack2(3.27762635e-03f, 3.27762635e-03f));
+  p = fma2(p, ax, pack2(2.11410057e-02f, 2.11410057e-02f));
+  p = fma2(p, ax, pack2(4.98673469e-02f, 4.98673469e-02f));
+  p = fma2(p, ax, pack2(1.0f, 1.0f));
+  p = mul2(p, p);
+  p = mul2(p, p);
+  p = mul2(p, p);
+  p = mul2(p, p);  // (1 + ...)^16 ; overflows to +inf for |x| > ~25, whose reciprocal is the correct 0
+  float p0, p1;
+  unpack2(p, p0, p1);
+  const uint64_t r = pack2(rcp_approx(p0), rcp_approx(p1));
+  const uint64_t relu = fma2(ax, pack2(0.5f, 0.5f), mul2(x, pack2(0.5f, 0.5f)));
+  unpack2(fma2(mul2(ax, pack2(-0.5f, -0.5f)), r, relu), x0, x1);
 }
 
 template <int BN, int EPI_WARPS>
@@ -101,7 +130,7 @@ struct EpStore {
     }
     if (p.act == 1) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+      for (int i = 0; i < 32; i += 2) gelu_erf2(f[i], f[i + 1]);
     }
     if (direct_residual && p.R && row_ok) {
       const __nv_bfloat16* r = p.R + (size_t)row * p.ldr + col0;

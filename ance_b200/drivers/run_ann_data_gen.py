@@ -347,7 +347,7 @@ def get_arguments(argv=None):
     # B200 knobs (not in the reference)
     p.add_argument("--search_operand", default="bf16", choices=["bf16", "fp16"],
                    help="16-bit operand format of the coarse tensor-core pass (results are exact either way)")
-    p.add_argument("--encode_batch_tokens", default=65536, type=int, help="tokens per encoder launch sequence")
+    p.add_argument("--encode_batch_tokens", default=75776, type=int, help="tokens per encoder launch sequence")
     p.add_argument("--reference_sampling", default=False, action="store_true",
                    help="draw the negative-sampling order from Python's `random` exactly as the reference does")
     p.add_argument("--seed", default=None, type=int, help="seed for the sampling order (reference: unseeded)")

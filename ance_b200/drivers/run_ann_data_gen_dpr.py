@@ -198,7 +198,7 @@ def get_arguments(argv=None):
     p.add_argument("--trivia_test_qa_path", default=None, type=str, required=True)
     # B200 knobs
     p.add_argument("--search_operand", default="bf16", choices=["bf16", "fp16"])
-    p.add_argument("--encode_batch_tokens", default=65536, type=int)
+    p.add_argument("--encode_batch_tokens", default=75776, type=int)
     p.add_argument("--seed", default=None, type=int)
     p.add_argument("--poll_seconds", default=60, type=int)
     a = p.parse_args(argv)

@@ -170,8 +170,9 @@ class _CudaEncoder:
 class _B200Encoder(nn.Module):
     """Common machinery: lazily (re)build the CUDA encoder when the parameters move or change."""
 
-    #: tokens processed per launch sequence (activations: ~14 KB per token)
-    max_tokens = int(os.environ.get("ANCE_B200_MAX_TOKENS", 65536))
+    #: tokens processed per launch sequence (activations: ~14 KB per token).  75,776 = 296 row blocks of 256:
+    #: every encoder GEMM then has a tile count divisible by the 74 CTA pairs of a B200 (no partial last wave).
+    max_tokens = int(os.environ.get("ANCE_B200_MAX_TOKENS", 75776))
 
     def _enc_for(self, name, backbone, arch, heads, pad_id, head, device) -> _CudaEncoder:
         if device.type != "cuda":

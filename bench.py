@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — ANN-refresh throughput (BASELINE.json metric) on N GPUs of one node.
 
-One STEP = one slice of a full refresh at the refresh's own passage:query mix (8,841,823 : 502,939 ~ 18:1):
+One STEP = one slice of a full refresh at the refresh's own passage:query mix (8,841,823 : 502,939 = 17.6:1; the step uses 16:1):
     encode PB passages (rdot_nll, RoBERTa-base, L=128, full-length synthetic token ids)
   + encode QB train queries (L=64)
   + top-200 inner-product search of those QB queries against the resident 8,841,823 x 768 index
@@ -376,8 +376,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--passages_per_step", type=int, default=36864)
-    ap.add_argument("--queries_per_step", type=int, default=2048)
+    ap.add_argument("--passages_per_step", type=int, default=37888)   # 64 encoder passes of 592 x 128 tokens
+    ap.add_argument("--queries_per_step", type=int, default=2368)     # 2 encoder passes of 1184 x 64 tokens (16:1)
     ap.add_argument("--search_operand", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
