@@ -25,6 +25,12 @@ using namespace tc05;
 constexpr int kTile = 128;   // query rows / keys per block
 constexpr int kDh = 64;      // head dim
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct Params {
   int n_tokens;        // B * L
   int L;               // sequence length
@@ -42,7 +48,7 @@ struct Smem {
   static constexpr int kV = kK + kStages * kTile * kDh * 2;
   static constexpr int kP = kV + kStages * kTile * kDh * 2;    // 128 x 128 bf16 (two 64-key halves)
   static constexpr int kBias = kP + kTile * kTile * 2;       // 128 floats
-  static constexpr int kBar = kBias + kTile * 4;
+  static constexpr int kBar = kBias + kTile * 4 + 16;
   // q_full q_empty kv_full[2] kv_empty[2] s p o  + tmem ptr
   static constexpr int kTotal = kBar + 9 * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;
@@ -63,6 +69,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
   uint64_t* bar_o = bars + 8;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
   float* sbias = reinterpret_cast<float*>(smem + Smem::kBias);
+  unsigned* smask = reinterpret_cast<unsigned*>(smem + Smem::kBias + kTile * 4);  // per-warp ballots of masked keys
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.n_tokens + kTile - 1) / kTile;
@@ -173,26 +180,37 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
         // all arrived on bar_p before the PV MMA whose completion we waited for below)
         {
           const int kt = kv_tok0 + j * kTile + tid128;
-          sbias[tid128] = (kt < p.n_tokens) ? __ldg(p.kbias + kt) : -INFINITY;
+          const float bv = (kt < p.n_tokens) ? __ldg(p.kbias + kt) : -INFINITY;
+          sbias[tid128] = bv;
+          const unsigned mk = __ballot_sync(0xffffffffu, bv < 0.f);
+          if (lane == 0) smask[warp - 4] = mk;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        // no key of this block carries a mask bias (and the tile is one sequence): the bias terms vanish
+        const bool plain = !kPacked && ((smask[0] | smask[1] | smask[2] | smask[3]) == 0u);
         mbar_wait(bar_s, it & 1, 15);
         tc_fence_after_sync();
-        // pass 1: row max
+        // pass 1: row max (of the raw scores when `plain`: scale > 0 commutes with max)
         float m_blk = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < kTile; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_S + lane_sel + c, v);
           tmem_ld_wait();
+          if (plain) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = c + i;
-            float t = fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[key]);
-            if (kPacked && (key < seq_lo || key >= seq_hi)) t = -INFINITY;
-            m_blk = fmaxf(m_blk, t);
+            for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int key = c + i;
+              float t = fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[key]);
+              if (kPacked && (key < seq_lo || key >= seq_hi)) t = -INFINITY;
+              m_blk = fmaxf(m_blk, t);
+            }
           }
         }
+        if (plain) m_blk *= p.scale_log2;
         const float m_new = fmaxf(m_run, m_blk);
         const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
         // pass 2: p = exp2(t - m_new), row sum, bf16 P into swizzled smem
@@ -203,16 +221,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
           tmem_ld_32x32b_x32(tmem_S + lane_sel + c, v);
           tmem_ld_wait();
           uint32_t pk[16];
+          if (plain) {
+            const float nm = -m_new;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float t0 = fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[c + i]);
-            float t1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, sbias[c + i + 1]);
-            if (kPacked && (c + i < seq_lo || c + i >= seq_hi)) t0 = -INFINITY;
-            if (kPacked && (c + i + 1 < seq_lo || c + i + 1 >= seq_hi)) t1 = -INFINITY;
-            const float p0 = exp2f(t0 - m_new), p1 = exp2f(t1 - m_new);
-            rsum += p0 + p1;
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = ex2_ftz(fmaf(__uint_as_float(v[i]), p.scale_log2, nm));
+              const float p1 = ex2_ftz(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, nm));
+              rsum += p0 + p1;
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+              pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float t0 = fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[c + i]);
+              float t1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, sbias[c + i + 1]);
+              if (kPacked && (c + i < seq_lo || c + i >= seq_hi)) t0 = -INFINITY;
+              if (kPacked && (c + i + 1 < seq_lo || c + i + 1 >= seq_hi)) t1 = -INFINITY;
+              const float p0 = ex2_ftz(t0 - m_new), p1 = ex2_ftz(t1 - m_new);
+              rsum += p0 + p1;
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+              pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
           }
           // four 16-byte chunks (8 keys each); swizzle: chunk index ^= (row & 7) inside the 128-byte span
           const int half = c >> 6;                 // which 64-key half

@@ -243,6 +243,7 @@ struct ance_encoder {
   int* err_flag = nullptr;
   __nv_bfloat16* dbg = nullptr;  // [(n_layer+1), max_tokens, H] when debugging
   int dbg_tokens = 0;
+  int prune_last_layer = 1;  // last layer: only the CLS rows go through out-proj / FFN (identical result)
   std::vector<void*> allocs;
 };
 
@@ -272,7 +273,8 @@ __nv_bfloat16* upload_bf16(ance_encoder* e, const float* h, size_t n) {
 
 // one GEMM of the forward: C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ R)
 int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, int N, int K, const float* bias,
-           const __nv_bfloat16* R, int act, __nv_bfloat16* C, float* C32, cudaStream_t st, int cls = ance::kClsGemm) {
+           const __nv_bfloat16* R, int act, __nv_bfloat16* C, float* C32, cudaStream_t st, int cls = ance::kClsGemm,
+           size_t ldr = 0) {
   constexpr int BN = 256, EW = 8, CG = 2, STAGES = 6;  // cta_group::2: 256 x 256 tile per CTA pair
   using Ep = gemm::EpStore<BN, EW>;
   CUtensorMap tmA, tmB;
@@ -287,7 +289,8 @@ int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, in
     ance::set_error("encoder: cuTensorMapEncodeTiled failed for the output (M=%d N=%d)", M, N);
     return ANCE_ERR_CUDA;
   }
-  if (C && R && !gemm::make_store_tmap(&p.tmR, const_cast<__nv_bfloat16*>(R), M, N, N)) {
+  if (ldr == 0) ldr = N;
+  if (C && R && !gemm::make_store_tmap(&p.tmR, const_cast<__nv_bfloat16*>(R), M, N, static_cast<int>(ldr))) {
     ance::set_error("encoder: cuTensorMapEncodeTiled failed for the residual (M=%d N=%d)", M, N);
     return ANCE_ERR_CUDA;
   }
@@ -297,7 +300,7 @@ int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, in
   p.R = R;
   p.ldc = N;
   p.ldc32 = N;
-  p.ldr = N;
+  p.ldr = static_cast<int>(ldr);
   p.act = act;
   {
     ance::ProfScope ps(cls, st);
@@ -474,25 +477,38 @@ extern "C" int ance_encoder_forward(ance_encoder_t e, const int32_t* ids_dev, co
     ance::prof_end(ance::kClsAttn, st);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(1);
-    if ((rc = linear(e->CTX, H, M, d.wo, H, H, d.bo, e->X, 0, e->T, nullptr, st, ance::kClsGemmOut))) return rc;
-    if ((rc = layer_norm(e->T, false, H, M, H, d.ln1g, d.ln1b, c.ln_eps, e->X1, nullptr, st))) return rc;
-    if ((rc = linear(e->X1, H, M, d.w1, F, H, d.b1, nullptr, 1, e->FF, nullptr, st, ance::kClsGemmFfn1))) return rc;
-    if ((rc = linear(e->FF, F, M, d.w2, H, F, d.b2, e->X1, 0, e->T, nullptr, st, ance::kClsGemmFfn2))) return rc;
-    if ((rc = layer_norm(e->T, false, H, M, H, d.ln2g, d.ln2b, c.ln_eps, e->X, nullptr, st))) return rc;
-    if (e->dbg && M <= e->dbg_tokens)
-      ANCE_CUDA(cudaMemcpyAsync(e->dbg + static_cast<size_t>(l + 1) * e->dbg_tokens * H, e->X, static_cast<size_t>(M) * H * 2, cudaMemcpyDeviceToDevice, st));
+    // In the last layer only token 0 of every sequence is read downstream (models.py:49,193): run the
+    // out-projection, FFN and both LayerNorms on those B rows only (strided TMA views, compact outputs).
+    const bool cls_only = e->prune_last_layer && (l == c.n_layer - 1);
+    const int Mr = cls_only ? B : M;                                    // rows processed from here on
+    const size_t pitch = cls_only ? static_cast<size_t>(L) * H : H;     // row pitch of CTX / X views
+    if ((rc = linear(e->CTX, pitch, Mr, d.wo, H, H, d.bo, e->X, 0, e->T, nullptr, st, ance::kClsGemmOut, pitch))) return rc;
+    if ((rc = layer_norm(e->T, false, H, Mr, H, d.ln1g, d.ln1b, c.ln_eps, e->X1, nullptr, st))) return rc;
+    if ((rc = linear(e->X1, H, Mr, d.w1, F, H, d.b1, nullptr, 1, e->FF, nullptr, st, ance::kClsGemmFfn1))) return rc;
+    if ((rc = linear(e->FF, F, Mr, d.w2, H, F, d.b2, e->X1, 0, e->T, nullptr, st, ance::kClsGemmFfn2))) return rc;
+    if ((rc = layer_norm(e->T, false, H, Mr, H, d.ln2g, d.ln2b, c.ln_eps, e->X, nullptr, st))) return rc;
+    if (e->dbg && M <= e->dbg_tokens)  // with cls_only the first B rows hold the CLS rows of the last layer
+      ANCE_CUDA(cudaMemcpyAsync(e->dbg + static_cast<size_t>(l + 1) * e->dbg_tokens * H, e->X, static_cast<size_t>(Mr) * H * 2, cudaMemcpyDeviceToDevice, st));
   }
+  const size_t cls_pitch = e->prune_last_layer ? static_cast<size_t>(H) : static_cast<size_t>(L) * H;
   // K7: CLS rows (token 0 of every sequence) -> head
   if (c.has_head) {
-    // A = X viewed as [B, H] with row pitch L*H
-    if ((rc = linear(e->X, static_cast<size_t>(L) * H, B, e->head_w, H, H, e->head_b, nullptr, 0, nullptr, e->head_tmp, st))) return rc;
+    // A = the CLS rows of X ([B, H] compact after the pruned last layer, else row pitch L*H)
+    if ((rc = linear(e->X, cls_pitch, B, e->head_w, H, H, e->head_b, nullptr, 0, nullptr, e->head_tmp, st))) return rc;
     if ((rc = layer_norm(e->head_tmp, true, H, B, H, e->head_g, e->head_bt, 1e-5f, nullptr, out_dev, st))) return rc;
   } else {
     ance::ProfScope ps(ance::kClsNorm, st);
-    gather_rows_f32_kernel<<<B, 256, 0, st>>>(e->X, static_cast<size_t>(L) * H, B, H, out_dev);
+    gather_rows_f32_kernel<<<B, 256, 0, st>>>(e->X, cls_pitch, B, H, out_dev);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(1);
   }
+  return ANCE_OK;
+}
+
+extern "C" int ance_encoder_set_param(ance_encoder_t e, const char* name, double value) {
+  ANCE_REQUIRE(e != nullptr && name != nullptr, "ance_encoder_set_param: null argument");
+  if (!strcmp(name, "prune_last_layer")) e->prune_last_layer = value != 0;
+  else { ance::set_error("ance_encoder_set_param: unknown parameter '%s'", name); return ANCE_ERR_INVALID; }
   return ANCE_OK;
 }
 

@@ -717,8 +717,19 @@ int coarse_rescore_pass(ance_index* ix, const uint16_t* Q16, const float* q_f32,
   const int q_tiles = static_cast<int>((nq + gemm::BM * cg - 1) / (gemm::BM * cg));
   int n_splits = n_splits_req;
   if (n_splits == 0) {
-    // enough work items to fill the machine twice over when there are few query tiles
-    n_splits = (q_tiles >= 2 * clusters) ? 1 : std::min(16, (2 * clusters + q_tiles - 1) / q_tiles);
+    // Few query tiles: split the corpus into row ranges so that every CTA (pair) has work, choosing the
+    // split count whose work-item count fills whole waves best (ties: fewer splits = fewer candidates).
+    n_splits = 1;
+    if (q_tiles < 2 * clusters) {
+      const int max_splits = std::max(1, std::min(16, 4096 / kprime));
+      double best = -1.0;
+      for (int sp = 1; sp <= max_splits; ++sp) {
+        const long items = static_cast<long>(q_tiles) * sp;
+        const long waves = (items + clusters - 1) / clusters;
+        const double eff = static_cast<double>(items) / static_cast<double>(waves * clusters);
+        if (eff > best + 1e-9) { best = eff; n_splits = sp; }
+      }
+    }
   }
   while (n_splits > 1 && n_splits * kprime > 4096) --n_splits;
   ANCE_REQUIRE(n_splits * kprime <= 4096, "ance_index_search: n_splits * kprime = %d exceeds 4096", n_splits * kprime);

@@ -141,6 +141,9 @@ class _CudaEncoder:
         except Exception:
             pass
 
+    def set_param(self, name: str, value: float):
+        _lib.check(self.lib.ance_encoder_set_param(self.h, name.encode(), float(value)))
+
     def enable_debug(self):
         """Capture hidden states of batches up to 4096 tokens (parity tests only)."""
         _lib.check(self.lib.ance_encoder_debug_hidden(self.h, -1, None, None))

@@ -124,8 +124,12 @@ int ance_encoder_destroy(ance_encoder_t enc);
  * finite "uniform attention" vector the reference yields.  out_dev [B, hidden] fp32. */
 int ance_encoder_forward(ance_encoder_t enc, const int32_t* ids_dev, const int32_t* lens_dev,
                          const uint8_t* mask_dev, int B, int L, float* out_dev, void* stream);
+/* Tunables: "prune_last_layer" (default 1): in the last layer only token 0 of every sequence is read
+ * downstream, so out-projection / FFN / LayerNorm run on those rows only (result-identical; bench.py reports
+ * the executed FLOPs beside the algorithmic ones). */
+int ance_encoder_set_param(ance_encoder_t enc, const char* name, double value);
 /* Debug / parity: copy the hidden states after layer `layer` (0 = embeddings) of the last forward
- * into out_dev [B*L, hidden] fp32. */
+ * into out_dev [B*L, hidden] fp32 (with prune_last_layer the last layer holds its B CLS rows first). */
 int ance_encoder_debug_hidden(ance_encoder_t enc, int layer, float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

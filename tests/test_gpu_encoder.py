@@ -68,8 +68,18 @@ def test_layer_by_layer_vs_oracle(rdot, golden_dir):
     m = torch.from_numpy(mask.reshape(-1))
     for l in range(13):
         h = enc.hidden(l, ids.size).cpu()
-        d = (h - hs[l].reshape(ids.size, -1)).abs()[m]   # real tokens; pad positions are never read downstream
+        if l < 12:
+            d = (h - hs[l].reshape(ids.size, -1)).abs()[m]   # real tokens; pad positions are never read downstream
+        else:  # pruned last layer: the first B rows are the CLS rows (the only ones the head reads)
+            h = h[:ids.shape[0]]
+            d = (h - hs[l][:, 0]).abs()
         assert not torch.isnan(h).any() and d.max().item() <= MAXABS, f"layer {l}: {d.max().item()}"
+    # pruning the last layer to the CLS rows does not change the embeddings
+    pruned = model.encode_lens(torch.from_numpy(ids).cuda(), torch.from_numpy(lens).cuda())
+    enc.set_param("prune_last_layer", 0)
+    full = model.encode_lens(torch.from_numpy(ids).cuda(), torch.from_numpy(lens).cuda())
+    enc.set_param("prune_last_layer", 1)
+    assert torch.equal(pruned, full)
 
 
 def test_ragged_batch_and_batch_invariance(rdot):
