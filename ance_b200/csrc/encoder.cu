@@ -137,88 +137,71 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const EmbedParams p) {
 // LayerNorm over rows: bf16 or fp32 in, bf16 and/or fp32 out; row r read at in + r * in_ld
 // ------------------------------------------------------------------------------------------------
 template <int NV, bool kInF32>
-struct LnRow {
-  float x[NV * 8];
-  __device__ __forceinline__ void load(const void* in, size_t in_ld, int row, int lane) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int col = (v * 32 + lane) * 8;
-      if (kInF32) {
-        const float* r = reinterpret_cast<const float*>(in) + static_cast<size_t>(row) * in_ld + col;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(r)), b = __ldg(reinterpret_cast<const float4*>(r + 4));
-        x[v * 8 + 0] = a.x; x[v * 8 + 1] = a.y; x[v * 8 + 2] = a.z; x[v * 8 + 3] = a.w;
-        x[v * 8 + 4] = b.x; x[v * 8 + 5] = b.y; x[v * 8 + 6] = b.z; x[v * 8 + 7] = b.w;
-      } else {
-        const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(in) + static_cast<size_t>(row) * in_ld + col;
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(r));
-        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = __bfloat1622float2(ah[q]);
-          x[v * 8 + q * 2] = f.x;
-          x[v * 8 + q * 2 + 1] = f.y;
-        }
-      }
-    }
-  }
-};
-
-// One warp per row, grid-stride over rows with the NEXT row's loads issued before the current row's
-// reductions (the kernel is HBM/L2-bound: bytes in flight are what matters).
-template <int NV, bool kInF32>
-__global__ void __launch_bounds__(256, 4) ln_rows_kernel(const void* __restrict__ in, size_t in_ld, int n_rows, int H,
+__global__ void __launch_bounds__(256) ln_rows_kernel(const void* __restrict__ in, size_t in_ld, int n_rows, int H,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       float eps, __nv_bfloat16* __restrict__ out16,
                                                       float* __restrict__ out32) {
   const int lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * 8;
-  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n_rows) return;
-  LnRow<NV, kInF32> cur, nxt;
-  cur.load(in, in_ld, row, lane);
-  for (; row < n_rows; row += warps_total) {
-    const int next_row = row + warps_total;
-    if (next_row < n_rows) nxt.load(in, in_ld, next_row, lane);
-    float sum = 0.f;
+  float x[NV * 8];
+  float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV * 8; ++i) sum += cur.x[i];
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    if (kInF32) {
+      const float* r = reinterpret_cast<const float*>(in) + static_cast<size_t>(row) * in_ld + col;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(r)), b = __ldg(reinterpret_cast<const float4*>(r + 4));
+      x[v * 8 + 0] = a.x; x[v * 8 + 1] = a.y; x[v * 8 + 2] = a.z; x[v * 8 + 3] = a.w;
+      x[v * 8 + 4] = b.x; x[v * 8 + 5] = b.y; x[v * 8 + 6] = b.z; x[v * 8 + 7] = b.w;
+    } else {
+      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(in) + static_cast<size_t>(row) * in_ld + col;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(r));
+      const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-    const float mean = sum / H;
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV * 8; ++i) {
-      const float d = cur.x[i] - mean;
-      var = fmaf(d, d, var);
-    }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
-    const float rstd = rsqrtf(var / H + eps);
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int col = (v * 32 + lane) * 8;
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float y[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = (cur.x[v * 8 + i] - mean) * rstd * g[i] + bb[i];
-      if (out16) {
-        uint4 u;
-        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(y[q * 2], y[q * 2 + 1]);
-        *reinterpret_cast<uint4*>(out16 + static_cast<size_t>(row) * H + col) = u;
-      }
-      if (out32) {
-        float* o = out32 + static_cast<size_t>(row) * H + col;
-        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(ah[q]);
+        x[v * 8 + q * 2] = f.x;
+        x[v * 8 + q * 2 + 1] = f.y;
       }
     }
 #pragma unroll
-    for (int i = 0; i < NV * 8; ++i) cur.x[i] = nxt.x[i];
+    for (int i = 0; i < 8; ++i) sum += x[v * 8 + i];
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const float mean = sum / H;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV * 8; ++i) {
+    const float d = x[i] - mean;
+    var = fmaf(d, d, var);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) var += __shfl_xor_sync(0xffffffffu, var, s);
+  const float rstd = rsqrtf(var / H + eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = (x[v * 8 + i] - mean) * rstd * g[i] + bb[i];
+    if (out16) {
+      uint4 u;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(y[q * 2], y[q * 2 + 1]);
+      *reinterpret_cast<uint4*>(out16 + static_cast<size_t>(row) * H + col) = u;
+    }
+    if (out32) {
+      float* o = out32 + static_cast<size_t>(row) * H + col;
+      *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    }
   }
 }
 
@@ -329,7 +312,7 @@ int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, in
 
 int layer_norm(const void* in, bool in_f32, size_t in_ld, int rows, int H, const float* g, const float* b, float eps,
                __nv_bfloat16* out16, float* out32, cudaStream_t st) {
-  const int blocks = std::min((rows + 7) / 8, gemm::sm_count() * 4);  // grid-stride over rows: 4 resident blocks of 8 warps per SM
+  const int blocks = (rows + 7) / 8;
   const int nv = H / 256;
   ance::ProfScope ps(ance::kClsNorm, st);
 #define LN_CASE(NV_)                                                                                       \
