@@ -34,6 +34,7 @@ struct WorkShape {
   int num_n_blks;        // ceil(N / BN)
   int n_splits;          // work items per m block
   int n_blks_per_split;  // ceil(num_n_blks / n_splits)
+  unsigned long long hint_a, hint_b;  // L2 cache-policy words of the A / B tile loads (0 = the epilogue's default)
 };
 
 struct EpiCtx {
@@ -110,6 +111,7 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      const uint64_t hint_a = ws.hint_a ? ws.hint_a : Ep::kHintA, hint_b = ws.hint_b ? ws.hint_b : Ep::kHintB;
       Ring<STAGES> ring;
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int m_blk = w / ws.n_splits, split = w - m_blk * ws.n_splits;
@@ -124,15 +126,15 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* sb = sa + Plan::kABytes;
             if constexpr (CG == 1) {
               mbar_arrive_expect_tx(&full_bar[ring.stage], Plan::kStageBytes);
-              tma_load_2d(sa, &tmA, &full_bar[ring.stage], kb * BK, a_row, Ep::kHintA);
-              tma_load_2d(sb, &tmB, &full_bar[ring.stage], kb * BK, b_row, Ep::kHintB);
+              tma_load_2d(sa, &tmA, &full_bar[ring.stage], kb * BK, a_row, hint_a);
+              tma_load_2d(sb, &tmB, &full_bar[ring.stage], kb * BK, b_row, hint_b);
             } else {
               // Both CTAs' TMA bytes complete on the LEADER's barrier; only the leader arrives on it.  The
               // peer cannot run a phase ahead: it refills a stage only after the MMA that consumed it
               // (multicast commit on its own empty barrier).
               if (leader) mbar_arrive_expect_tx(&full_bar[ring.stage], 2 * Plan::kStageBytes);
-              tma_load_2d_2sm(sa, &tmA, &full_bar[ring.stage], kb * BK, a_row, Ep::kHintA);
-              tma_load_2d_2sm(sb, &tmB, &full_bar[ring.stage], kb * BK, b_row, Ep::kHintB);
+              tma_load_2d_2sm(sa, &tmA, &full_bar[ring.stage], kb * BK, a_row, hint_a);
+              tma_load_2d_2sm(sb, &tmB, &full_bar[ring.stage], kb * BK, b_row, hint_b);
             }
             ring.advance();
           }
@@ -266,6 +268,7 @@ inline WorkShape make_shape(int M, int N, int K, int BN, int CG, int n_splits /*
   if (n_splits <= 0 || n_splits > ws.num_n_blks) n_splits = ws.num_n_blks;
   ws.n_blks_per_split = (ws.num_n_blks + n_splits - 1) / n_splits;
   ws.n_splits = (ws.num_n_blks + ws.n_blks_per_split - 1) / ws.n_blks_per_split;
+  ws.hint_a = ws.hint_b = 0;
   return ws;
 }
 

@@ -131,7 +131,9 @@ __global__ void quantize_rows_kernel(const float* __restrict__ X, uint16_t* __re
 template <int BN, int CAP>
 struct EpTopK {
   static constexpr uint64_t kHintA = tc05::kEvictLast;   // query tile: re-read for every corpus tile
-  static constexpr uint64_t kHintB = tc05::kEvictFirst;  // corpus rows: streamed once per sweep
+  static constexpr uint64_t kHintB = tc05::kEvictNormal;  // corpus rows: every concurrently sweeping CTA pair re-reads
+                                                          // the same tile from L2 (EVICT_FIRST made each pair go to
+                                                          // HBM: 788 GB of DRAM reads for 13.6 GB of operands, ncu r01)
   static constexpr int kSlots = CAP / 32;
   static constexpr int kSmemBytes = 0;
   struct Params {
@@ -625,6 +627,9 @@ int launch_coarse(ance_index* ix, const uint16_t* Q16, int64_t nq, int kprime, i
   const int N = static_cast<int>(ix->n);
   gemm::WorkShape ws = gemm::make_shape(static_cast<int>(nq), N, ix->dim, BN, CG, n_splits_req);
   *n_splits_out = ws.n_splits;
+  // One sweep per query tile: every concurrently running CTA pair re-reads the same corpus tile, so keep it in L2.
+  // With row-range splits each pair streams its own range once: do not let it evict the (re-read) query tiles.
+  ws.hint_b = (ws.n_splits == 1) ? tc05::kEvictNormal : tc05::kEvictFirst;
   CUtensorMap tmA, tmB;
   if (!tc05_host::make_tmap_2d_16b(&tmA, Q16, nq, ix->dim, ix->dim, gemm::BM) ||
       !tc05_host::make_tmap_2d_16b(&tmB, ix->P16, ix->n, ix->dim, ix->dim, BN / CG)) {
