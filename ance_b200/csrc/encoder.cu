@@ -406,8 +406,9 @@ extern "C" int ance_encoder_create(const ance_encoder_config* cfg, const ance_en
   cudaMemset(e->err_flag, 0, sizeof(int));
   static bool attr = false;
   if (!attr) {
-    ANCE_CUDA(cudaFuncSetAttribute(attn::attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Smem::kDynamic));
-    ANCE_CUDA(cudaFuncSetAttribute(attn::attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Smem::kDynamic));
+    ANCE_CUDA(cudaFuncSetAttribute(attn::attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Smem::kDynamic));
+    ANCE_CUDA(cudaFuncSetAttribute(attn::attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Smem::kDynamic));
+    ANCE_CUDA(cudaFuncSetAttribute(attn::attention_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::Smem::kDynamic));
     attr = true;
   }
   *out = e;
@@ -462,18 +463,24 @@ extern "C" int ance_encoder_forward(ance_encoder_t e, const int32_t* ids_dev, co
     ance::set_error("encoder: cuTensorMapEncodeTiled failed for QKV");
     return ANCE_ERR_CUDA;
   }
+  CUtensorMap tmCTX;
+  if (!tc05_host::make_tmap_2d_16b(&tmCTX, e->CTX, M, H, H, attn::kTile)) {
+    ance::set_error("encoder: cuTensorMapEncodeTiled failed for the attention output");
+    return ANCE_ERR_CUDA;
+  }
   attn::Params ap;
   ap.n_tokens = M; ap.L = L; ap.heads = c.heads; ap.hidden = H;
-  ap.kbias = e->kbias; ap.ctx = e->CTX;
+  ap.kbias = e->kbias;
   ap.scale_log2 = kLog2e / 8.0f;
   const int attn_work = ((M + 127) / 128) * c.heads;
-  const int attn_grid = std::min(attn_work, 2 * gemm::sm_count());
+  const int attn_grid = std::min(attn_work, gemm::sm_count());
   for (int l = 0; l < c.n_layer; ++l) {
     const LayerDev& d = e->layers[l];
     if ((rc = linear(e->X, H, M, d.wqkv, 3 * H, H, d.bqkv, nullptr, 0, e->QKV, nullptr, st, ance::kClsGemmQkv))) return rc;
     ance::prof_begin(ance::kClsAttn, st);
-    if (L < attn::kTile) attn::attention_kernel<true><<<attn_grid, 256, attn::Smem::kDynamic, st>>>(tmQKV, ap);
-    else attn::attention_kernel<false><<<attn_grid, 256, attn::Smem::kDynamic, st>>>(tmQKV, ap);
+    if (L < attn::kTile) attn::attention_kernel<true, true><<<attn_grid, attn::kThreads, attn::Smem::kDynamic, st>>>(tmQKV, tmCTX, ap);
+    else if (L == attn::kTile) attn::attention_kernel<false, true><<<attn_grid, attn::kThreads, attn::Smem::kDynamic, st>>>(tmQKV, tmCTX, ap);
+    else attn::attention_kernel<false, false><<<attn_grid, attn::kThreads, attn::Smem::kDynamic, st>>>(tmQKV, tmCTX, ap);
     ance::prof_end(ance::kClsAttn, st);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(1);
@@ -509,6 +516,20 @@ extern "C" int ance_encoder_set_param(ance_encoder_t e, const char* name, double
   ANCE_REQUIRE(e != nullptr && name != nullptr, "ance_encoder_set_param: null argument");
   if (!strcmp(name, "prune_last_layer")) e->prune_last_layer = value != 0;
   else { ance::set_error("ance_encoder_set_param: unknown parameter '%s'", name); return ANCE_ERR_INVALID; }
+  return ANCE_OK;
+}
+
+extern "C" int ance_encoder_check(ance_encoder_t e, void* stream) {
+  ANCE_REQUIRE(e != nullptr, "ance_encoder_check: null handle");
+  int err = 0;
+  ANCE_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  ANCE_CUDA(cudaMemcpy(&err, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) {
+    ANCE_CUDA(cudaMemset(e->err_flag, 0, sizeof(int)));
+    ance::set_error("ance_encoder_forward: a token id outside [0, vocab_size) or a position past max_position_embeddings "
+                    "was seen since the last check (the reference's embedding lookup raises an index error there)");
+    return ANCE_ERR_INVALID;
+  }
   return ANCE_OK;
 }
 

@@ -177,6 +177,8 @@ class B200Backend:
                     e, i = self.model.encode_lens(ids_d, lens_d), idx.numpy()
                 outs.append(e)
                 ids_out.append(i)
+        if hasattr(self.model, "check_inputs"):
+            self.model.check_inputs()   # out-of-vocabulary ids: fail like the reference's embedding lookup does
         if outs:
             return torch.cat(outs, dim=0), np.concatenate(ids_out)
         return torch.empty((0, 768), dtype=torch.float32, device=self.device), np.empty((0,), dtype=np.int64)

@@ -144,6 +144,11 @@ class _CudaEncoder:
     def set_param(self, name: str, value: float):
         _lib.check(self.lib.ance_encoder_set_param(self.h, name.encode(), float(value)))
 
+    def check(self):
+        """Raise if any forward since the last check saw an out-of-range token id / position (synchronises)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ance_encoder_check(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
     def enable_debug(self):
         """Capture hidden states of batches up to 4096 tokens (parity tests only)."""
         _lib.check(self.lib.ance_encoder_debug_hidden(self.h, -1, None, None))
@@ -187,6 +192,13 @@ class _B200Encoder(nn.Module):
         if hit is None or hit[0] != ver:
             cache[name] = (ver, _CudaEncoder(backbone, arch, heads, pad_id, head, self.max_tokens, device))
         return cache[name][1]
+
+    def check_inputs(self) -> None:
+        """Deferred input validation (keeps `body_emb`/`query_emb` asynchronous): raises if any encode since the last
+        call saw a token id outside the vocabulary or a position beyond max_position_embeddings, where the reference's
+        nn.Embedding lookup raises an IndexError.  Synchronises the current stream; the drivers call it per pass."""
+        for _, enc in self.__dict__.get("_enc_cache", {}).values():
+            enc.check()
 
     @staticmethod
     def _prep(input_ids, attention_mask):

@@ -128,6 +128,12 @@ int ance_encoder_forward(ance_encoder_t enc, const int32_t* ids_dev, const int32
  * downstream, so out-projection / FFN / LayerNorm run on those rows only (result-identical; bench.py reports
  * the executed FLOPs beside the algorithmic ones). */
 int ance_encoder_set_param(ance_encoder_t enc, const char* name, double value);
+/* Input validation, deferred so that forward stays asynchronous: synchronises `stream` and returns
+ * ANCE_ERR_INVALID if any forward since the last check saw a token id outside [0, vocab_size) or a position
+ * beyond max_position_embeddings (such lookups are clamped on the device; the reference's nn.Embedding raises
+ * an index error, model/models.py:150-155 -> transformers modeling_roberta.py embeddings).  The drivers call it
+ * once per encode pass. */
+int ance_encoder_check(ance_encoder_t enc, void* stream);
 /* Debug / parity: copy the hidden states after layer `layer` (0 = embeddings) of the last forward
  * into out_dev [B*L, hidden] fp32 (with prune_last_layer the last layer holds its B CLS rows first). */
 int ance_encoder_debug_hidden(ance_encoder_t enc, int layer, float* out_dev, void* stream);

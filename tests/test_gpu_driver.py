@@ -105,6 +105,66 @@ def test_refresh_end_to_end(tmp_path):
     assert drv.get_latest_ann_data(str(out))[0] == 0
 
 
+def test_maxp_refresh_end_to_end(tmp_path):
+    """BASELINE config 4 in miniature: rdot_nll_multi_chunk, documents of 4 x 512 tokens, one index row per chunk
+    in the reference's chunk-major-per-batch order (run_ann_data_gen.py:183-186), pid de-duplication downstream."""
+    from transformers import RobertaConfig
+    from ance_b200.drivers import run_ann_data_gen as drv
+    rng = np.random.default_rng(1)
+    vocab, n_layer, n_d, n_q, n_dev = 2000, 2, 150, 40, 12
+    data = tmp_path / "data"
+    data.mkdir()
+    dlens = np.clip(rng.lognormal(6.6, 0.8, size=n_d).astype(int), 20, 2048)   # many documents leave chunks all-pad
+    dids = np.full((n_d, 2048), 1, dtype=np.int32)
+    for i, m in enumerate(dlens):
+        dids[i, :m] = rng.integers(3, vocab, size=m)
+        dids[i, 0] = 0
+    refresh_oracle.write_cache(str(data / "passages"), dlens, dids)
+    for name, n in (("train-query", n_q), ("dev-query", n_dev)):
+        lens = rng.integers(4, 20, size=n)
+        ids = np.full((n, 64), 1, dtype=np.int32)
+        for i, m in enumerate(lens):
+            ids[i, :m] = rng.integers(3, vocab, size=m)
+            ids[i, 0] = 0
+        refresh_oracle.write_cache(str(data / name), lens, ids)
+    train_pos = {q: int(rng.integers(0, n_d)) for q in range(n_q)}
+    with open(data / "train-qrel.tsv", "w") as f:
+        for q, p in train_pos.items():
+            f.write(f"{q}\t{p}\t1\n")
+    with open(data / "dev-qrel.tsv", "w") as f:
+        for q in range(n_dev):
+            f.write(f"{q}\t{int(rng.integers(0, n_d))}\t1\n")
+    ckpt = tmp_path / "init_model"
+    ckpt.mkdir()
+    RobertaConfig(vocab_size=vocab, hidden_size=768, num_hidden_layers=n_layer, num_attention_heads=12,
+                  intermediate_size=3072, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5,
+                  pad_token_id=1, bos_token_id=0, eos_token_id=2).save_pretrained(str(ckpt))
+    torch.save(random_roberta_state_dict(seed=6, n_layer=n_layer, vocab=vocab), str(ckpt / "pytorch_model.bin"))
+    out = tmp_path / "ann"
+    argv = ["--data_dir", str(data), "--training_dir", str(tmp_path / "none"), "--init_model_dir", str(ckpt),
+            "--model_type", "rdot_nll_multi_chunk", "--output_dir", str(out), "--cache_dir", str(tmp_path / "c"),
+            "--end_output_num", "0", "--max_seq_length", "2048", "--max_query_length", "64",
+            "--per_gpu_eval_batch_size", "16", "--topk_training", "40", "--negative_sample", "5",
+            "--ann_chunk_factor", "1", "--reference_sampling", "--seed", "0"]
+    drv.main(argv)
+    args = drv.get_arguments(argv)
+    drv.set_env(args)
+    _, _, model = drv.load_model(args, str(ckpt))
+    be = drv.B200Backend(args, model)
+    P, p2id = be.encode(str(data / "passages"), False)
+    assert P.shape == (n_d * 4, 768)
+    assert p2id.tolist() == refresh_oracle.rank_embedding2id(n_d, 1, 0, 16, chunks=4)   # chunk-major per batch of 16
+    Q, q2id = be.encode(str(data / "train-query"), True)
+    _, I = flat_ip_oracle.search(P.cpu().numpy(), Q.cpu().numpy(), 40)
+    rng2 = random.Random(0)
+    negs, _, _ = refresh_oracle.generate_negatives(q2id, p2id, train_pos, I, set(q2id.tolist()), 5, False, rng2)
+    want = "".join(refresh_oracle.training_data_lines(q2id, train_pos, negs, set(q2id.tolist()), rng2))
+    assert open(out / "ann_training_data_0").read() == want
+    for ln in want.splitlines():   # de-duplicated document ids
+        n = ln.split("\t")[2].split(",")
+        assert len(set(n)) == len(n)
+
+
 def test_inference_dumps(tmp_path):
     from ance_b200.drivers import run_ann_data_gen as drv
     data, ckpt, caches, *_ = _make_world(tmp_path, n_p=300, n_q=20, n_dev=10)

@@ -155,3 +155,12 @@ def test_bad_inputs(rdot):
                           torch.ones(2, dtype=torch.int32, device="cuda"))
     with pytest.raises(AnceError):
         model.query_emb(torch.zeros(1, 64, dtype=torch.long), torch.ones(1, 64, dtype=torch.long))  # CPU tensors
+    # a token id outside the vocabulary: the reference's nn.Embedding raises; here the check is deferred
+    ids = torch.zeros(2, 64, dtype=torch.int32, device="cuda")
+    ids[1, 3] = 60000
+    model.check_inputs()                       # clean so far
+    model.encode_lens(ids, torch.full((2,), 8, dtype=torch.int32, device="cuda"))
+    with pytest.raises(AnceError):
+        model.check_inputs()
+    model.check_inputs()                       # the flag is cleared once reported
+

@@ -61,6 +61,19 @@ def test_seeded_parity(operand, cta_group, k):
     assert np.abs(D - ref).max() <= 1e-3 * np.abs(ref).max()
 
 
+def test_default_topk_training_500():
+    """`--topk_training` defaults to 500 (run_ann_data_gen.py:556-560): the 2048-entry reservoir path (k' = 992)."""
+    rng = np.random.default_rng(21)
+    P = _ln_rows(rng, 50000, 768)
+    Q = _ln_rows(np.random.default_rng(22), 130, 768)
+    for k in (300, 500):
+        idx = _index(P)
+        D, I = idx.search(Q, k)
+        Do, Io = flat_ip_oracle.search(P, Q, k)
+        assert (I == Io).all() and (D == Do).all()
+        assert idx.stats()["kprime"] >= k
+
+
 def test_duplicates_and_ties_are_ordered_by_row():
     rng = np.random.default_rng(5)
     P = _ln_rows(rng, 20000, 768)

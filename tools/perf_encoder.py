@@ -21,11 +21,16 @@ def main():
     out = open(ROOT / "gpurun_out" / "perf_encoder.jsonl", "a")
     shapes = [(512, 128), (128, 512), (1024, 64), (256, 256)]
     if len(sys.argv) > 1:
-        shapes = [tuple(map(int, s.split("x"))) for s in sys.argv[1].split(",")]
-    for B, L in shapes:
+        shapes = [s for s in sys.argv[1].split(",")]
+    for shp in shapes:
+        ragged = isinstance(shp, str) and shp.endswith("r")   # "592x128r": lengths uniform in [L/8, L]
+        B, L = (tuple(map(int, shp.rstrip("r").split("x"))) if isinstance(shp, str) else shp)
         g = torch.Generator(device=dev).manual_seed(0)
         ids = torch.randint(3, 50265, (B, L), device=dev, generator=g, dtype=torch.int32)
         lens = torch.full((B,), L, device=dev, dtype=torch.int32)
+        if ragged:
+            lens = torch.randint(max(1, L // 8), L + 1, (B,), device=dev, generator=g, dtype=torch.int32)
+            ids = torch.where(torch.arange(L, device=dev)[None, :] < lens[:, None], ids, torch.ones_like(ids))
         for _ in range(3):
             model.encode_lens(ids, lens)
         torch.cuda.synchronize()
@@ -45,7 +50,7 @@ def main():
         _lib.profile_enable(False)
         gemm_flop = B * L * 12 * 24 * 768 * 768 + B * 2 * 768 * 768
         attn_flop = B * 12 * 4 * 768 * L * L
-        rec = {"B": B, "L": L, "ms": ms, "seq_per_s": B / ms * 1e3, "tflops_total": (gemm_flop + attn_flop) / ms / 1e9,
+        rec = {"B": B, "L": L, "ragged": ragged, "ms": ms, "seq_per_s": B / ms * 1e3, "tflops_total": (gemm_flop + attn_flop) / ms / 1e9,
                "gemm_ms": prof["encoder_gemm"][0] / it, "attn_ms": prof["attention"][0] / it,
                "norm_ms": prof["norm_embed"][0] / it,
                "gemm_tflops": gemm_flop / (prof["encoder_gemm"][0] / it) / 1e9,
