@@ -12,6 +12,7 @@
 //   T    = F W2^T + b2 + X1 ; X = LN(T)       GEMM with bias+residual epilogue, then ln_rows_kernel
 // Activations are bf16 in HBM; all accumulation, LayerNorm statistics and softmax are fp32.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -272,10 +273,15 @@ __nv_bfloat16* upload_bf16(ance_encoder* e, const float* h, size_t n) {
 }
 
 // one GEMM of the forward: C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ R)
-int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, int N, int K, const float* bias,
-           const __nv_bfloat16* R, int act, __nv_bfloat16* C, float* C32, cudaStream_t st, int cls = ance::kClsGemm,
-           size_t ldr = 0) {
-  constexpr int BN = 256, EW = 8, CG = 2, STAGES = 6;  // cta_group::2: 256 x 256 tile per CTA pair
+// cta_group::2: 256 x 256 tile per CTA pair.  EW = 8 epilogue warps (two 128-column groups, 6 smem stages) or EW = 16
+// (four 64-column groups, each with its own staging slab, 5 stages): with 16 a tile's epilogue is ONE
+// LDTM -> math -> TMA-store round per warp instead of two in sequence.  Measured at 592 x 128 (ms per forward, 8 -> 16):
+// FFN-up (GELU) 4.15 -> 3.62, out-proj 1.15 -> 1.06, but QKV 2.55 -> 2.90 and FFN-down 2.81 -> 2.90: the heavy / short-K
+// epilogues want the shorter chain, the light ones the deeper operand pipeline.
+template <int EW, int STAGES>
+int linear_cfg(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, int N, int K, const float* bias,
+               const __nv_bfloat16* R, int act, __nv_bfloat16* C, float* C32, cudaStream_t st, int cls, size_t ldr) {
+  constexpr int BN = 256, CG = 2;
   using Ep = gemm::EpStore<BN, EW>;
   CUtensorMap tmA, tmB;
   if (!tc05_host::make_tmap_2d_16b(&tmA, A, M, K, lda, gemm::BM) || !tc05_host::make_tmap_2d_16b(&tmB, W, N, K, K, BN / CG)) {
@@ -283,7 +289,7 @@ int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, in
     return ANCE_ERR_CUDA;
   }
   gemm::WorkShape ws = gemm::make_shape(M, N, K, BN, CG, 0);
-  Ep::Params p;
+  typename Ep::Params p;
   memset(&p, 0, sizeof(p));
   if (C && !gemm::make_store_tmap(&p.tmC, C, M, N, N)) {
     ance::set_error("encoder: cuTensorMapEncodeTiled failed for the output (M=%d N=%d)", M, N);
@@ -308,6 +314,16 @@ int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, in
   }
   ance::count_launch(1);
   return ANCE_OK;
+}
+
+int linear(const __nv_bfloat16* A, size_t lda, int M, const __nv_bfloat16* W, int N, int K, const float* bias,
+           const __nv_bfloat16* R, int act, __nv_bfloat16* C, float* C32, cudaStream_t st, int cls = ance::kClsGemm,
+           size_t ldr = 0) {
+  bool short_chain = (act != 0) || (R != nullptr && K <= 1024);   // FFN-up, out-proj
+  static const char* force = getenv("ANCE_B200_EPI_MASK");   // tuning aid: bit per GEMM class (qkv, out, ffn1, ffn2)
+  if (force && cls >= ance::kClsGemmQkv && cls <= ance::kClsGemmFfn2) short_chain = (atoi(force) >> (cls - ance::kClsGemmQkv)) & 1;
+  if (short_chain) return linear_cfg<16, 5>(A, lda, M, W, N, K, bias, R, act, C, C32, st, cls, ldr);
+  return linear_cfg<8, 6>(A, lda, M, W, N, K, bias, R, act, C, C32, st, cls, ldr);
 }
 
 int layer_norm(const void* in, bool in_f32, size_t in_ld, int rows, int H, const float* g, const float* b, float eps,

@@ -175,10 +175,12 @@ struct EpStore {
         tc05::mbar_arrive_expect_tx(rbar, kSlabBytes);
         tc05::tma_load_2d(slab, &p.tmR, rbar, col0, cx.row0, tc05::kEvictFirst);
       }
-      // both 32-column halves of the slab are requested from TMEM before the first is consumed
-      uint32_t va[32], vb[32];
+      // 8 epilogue warps (168 registers each): both 32-column halves of the slab are requested from TMEM before the
+      // first is consumed.  16 warps (102 registers each): one half at a time.
+      constexpr bool kLean = EPI_WARPS > 8;
+      uint32_t va[32], vb[kLean ? 1 : 32];
       tc05::tmem_ld_32x32b_x32(tacc + col_in_tile, va);
-      tc05::tmem_ld_32x32b_x32(tacc + col_in_tile + 32, vb);
+      if constexpr (!kLean) tc05::tmem_ld_32x32b_x32(tacc + col_in_tile + 32, vb);
       tc05::tmem_ld_wait();
       if (!tma_res && p.C) {
         // the slab is free once the previous TMA store has finished reading it
@@ -188,8 +190,17 @@ struct EpStore {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float f[32];
+        if constexpr (kLean) {
+          if (h == 1) {
+            tc05::tmem_ld_32x32b_x32(tacc + col_in_tile + 32, va);
+            tc05::tmem_ld_wait();
+          }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(h == 0 ? va[i] : vb[i]);
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(va[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(h == 0 ? va[i] : vb[i]);
+        }
         finish_chunk(p, ws, f, row, row_ok, col0 + h * 32, !tma_res);
         if (p.C32 && row_ok) {
           float* o = p.C32 + (size_t)row * p.ldc32 + col0 + h * 32;
