@@ -126,7 +126,8 @@ int ance_encoder_forward(ance_encoder_t enc, const int32_t* ids_dev, const int32
                          const uint8_t* mask_dev, int B, int L, float* out_dev, void* stream);
 /* Tunables: "prune_last_layer" (default 1): in the last layer only token 0 of every sequence is read
  * downstream, so out-projection / FFN / LayerNorm run on those rows only (result-identical; bench.py reports
- * the executed FLOPs beside the algorithmic ones). */
+ * the executed FLOPs beside the algorithmic ones).  "ln_rows_per_warp" (1, 2 or 4; default 2, process-wide): rows a warp
+ * of the LayerNorm kernel normalises side by side (bit-identical results; 2 is the fastest on B200). */
 int ance_encoder_set_param(ance_encoder_t enc, const char* name, double value);
 /* Input validation, deferred so that forward stays asynchronous: synchronises `stream` and returns
  * ANCE_ERR_INVALID if any forward since the last check saw a token id outside [0, vocab_size) or a position

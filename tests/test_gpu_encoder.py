@@ -164,3 +164,19 @@ def test_bad_inputs(rdot):
         model.check_inputs()
     model.check_inputs()                       # the flag is cleared once reported
 
+
+
+def test_layer_norm_rows_per_warp_variants_are_bit_identical(rdot):
+    model, _ = rdot
+    g = torch.Generator(device="cuda").manual_seed(3)
+    enc = model._encoder(torch.device("cuda:0"))
+    ids = torch.randint(3, 50265, (300, 128), device="cuda", generator=g, dtype=torch.int32)
+    lens = torch.randint(1, 129, (300,), device="cuda", generator=g, dtype=torch.int32)
+    outs = []
+    try:
+        for r in (1, 2, 4):
+            enc.set_param("ln_rows_per_warp", r)
+            outs.append(model.encode_lens(ids, lens).clone())
+    finally:
+        enc.set_param("ln_rows_per_warp", 2)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

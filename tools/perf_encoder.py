@@ -19,6 +19,9 @@ def main():
     model.load_state_dict(random_roberta_state_dict(seed=0), strict=True)
     model = model.to(dev).eval()
     out = open(ROOT / "gpurun_out" / "perf_encoder.jsonl", "a")
+    import os
+    if os.environ.get("ANCE_LN_ROWS"):
+        model._encoder(dev).set_param("ln_rows_per_warp", int(os.environ["ANCE_LN_ROWS"]))
     shapes = [(512, 128), (128, 512), (1024, 64), (256, 256)]
     if len(sys.argv) > 1:
         shapes = [s for s in sys.argv[1].split(",")]
