@@ -134,6 +134,96 @@ def GetProcessingFn(args, query=False):
     return fn
 
 
+def _parse_ann_line(line: str):
+    """`qid \\t pos_pid \\t neg,neg,...` -- the line grammar of ann_training_data_N (run_ann_data_gen.py:326-334)."""
+    a = line.split("\t")
+    return int(a[0]), int(a[1]), [int(x) for x in a[2].split(",")]
+
+
+def GetTrainingDataProcessingFn(args, query_cache, passage_cache):
+    """data/msmarco_data.py:306-334 (the trainer's side of the refresh protocol): one ANN line -> for every negative a
+    (query, positive, label 1) and a (query, negative, label 0) record."""
+    qfn, pfn = GetProcessingFn(args, query=True), GetProcessingFn(args, query=False)
+
+    def fn(line, i):
+        qid, pos_pid, neg_pids = _parse_ann_line(line)
+        q = qfn(query_cache[qid], qid)[0]
+        pos = pfn(passage_cache[pos_pid], pos_pid)[0]
+        pos_label, neg_label = torch.tensor(1, dtype=torch.long), torch.tensor(0, dtype=torch.long)
+        for neg_pid in neg_pids:
+            neg = pfn(passage_cache[neg_pid], neg_pid)[0]
+            yield (q[0], q[1], q[2], pos[0], pos[1], pos[2], pos_label)
+            yield (q[0], q[1], q[2], neg[0], neg[1], neg[2], neg_label)
+
+    return fn
+
+
+def GetTripletTrainingDataProcessingFn(args, query_cache, passage_cache):
+    """data/msmarco_data.py:337-362: one ANN line -> one (query, positive, negative) triplet per negative, the records
+    `run_ann.py:240-292` feeds to `model(*batch)`."""
+    qfn, pfn = GetProcessingFn(args, query=True), GetProcessingFn(args, query=False)
+
+    def fn(line, i):
+        qid, pos_pid, neg_pids = _parse_ann_line(line)
+        q = qfn(query_cache[qid], qid)[0]
+        pos = pfn(passage_cache[pos_pid], pos_pid)[0]
+        for neg_pid in neg_pids:
+            neg = pfn(passage_cache[neg_pid], neg_pid)[0]
+            yield (q[0], q[1], q[2], pos[0], pos[1], pos[2], neg[0], neg[1], neg[2])
+
+    return fn
+
+
+class TripletBatchReader:
+    """Bulk form of `StreamingDataset(lines, GetTripletTrainingDataProcessingFn(...))` + DataLoader(batch_size): the
+    triplets of this rank's ANN lines (line i -> rank i % world_size, utils/util.py:321-323), in the same order, as
+    pinned int32 id matrices and int32 lengths -- token rows come from the caches' memmaps in one vectorised gather per
+    batch instead of one 3-tensor TensorDataset per record.  Yields (q_ids, q_len, pos_ids, pos_len, neg_ids, neg_len)."""
+
+    def __init__(self, lines, query_cache: "EmbeddingCache", passage_cache: "EmbeddingCache", batch_size: int,
+                 max_query_length: int, max_seq_length: int, rank: int = 0, world_size: int = 1, pin: bool = True):
+        self.lines, self.qc, self.pc = lines, query_cache, passage_cache
+        self.batch_size, self.rank, self.world = int(batch_size), int(rank), int(world_size)
+        self.lq, self.lp = int(max_query_length), int(max_seq_length)
+        self.pin = pin and torch.cuda.is_available()
+
+    def _triplets(self):
+        for i, line in enumerate(self.lines):
+            if i % self.world != self.rank:
+                continue
+            qid, pos, negs = _parse_ann_line(line)
+            for n in negs:
+                yield qid, pos, n
+
+    @staticmethod
+    def _gather(mm, rows, L):
+        rec = mm[np.asarray(rows, dtype=np.int64)]
+        lens = rec["len"].astype(np.int32)
+        ids = np.ascontiguousarray(rec["ids"][:, :L]).astype(np.int32)
+        return ids, np.minimum(lens, L)
+
+    def __iter__(self):
+        qmm, pmm = self.qc.memmap(), self.pc.memmap()
+        buf = []
+
+        def emit(chunk):
+            cols = list(zip(*chunk))
+            out = []
+            for mm, rows, L in ((qmm, cols[0], self.lq), (pmm, cols[1], self.lp), (pmm, cols[2], self.lp)):
+                ids, lens = self._gather(mm, rows, L)
+                ti, tl = torch.from_numpy(ids), torch.from_numpy(lens)
+                out += [ti.pin_memory() if self.pin else ti, tl.pin_memory() if self.pin else tl]
+            return tuple(out)
+
+        for t in self._triplets():
+            buf.append(t)
+            if len(buf) == self.batch_size:
+                yield emit(buf)
+                buf = []
+        if buf:
+            yield emit(buf)
+
+
 def GetProcessingFnDPR(args, query=False):
     """data/DPR_data.py:276-296: as above but attention_mask = ids != 0 and token types all 0."""
 

@@ -208,9 +208,29 @@ class _B200Encoder(nn.Module):
         mask = (attention_mask != 0).to(torch.uint8).contiguous()
         return ids, mask
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("the training losses (reference model/models.py:58-134) are out of scope of "
-                                  "ance_b200; use the reference trainer for forward()/backward()")
+    # -- reference `NLL.forward` (model/models.py:58-84), EVALUATION ONLY ---------------------------------------
+    # Same signature and return values as the reference: embeddings when only one side is given, `(loss,)` for a
+    # (query, positive, negative) triplet batch.  The encoder kernels have no backward pass, so the loss carries no
+    # autograd graph (training stays with the reference trainer, SURVEY.md par. 8(f) row 3); it is what the trainer
+    # logs, computed with the refresher's weights.
+    @staticmethod
+    def _pair_logits(q_embs, x_embs, input_ids_x, attention_mask_x):
+        return (q_embs * x_embs).sum(-1)
+
+    @torch.no_grad()
+    def forward(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None, input_ids_b=None,
+                attention_mask_b=None, is_query=True):
+        if input_ids_b is None and is_query:
+            return self.query_emb(query_ids, attention_mask_q)
+        if input_ids_b is None:
+            return self.body_emb(query_ids, attention_mask_q)
+        q_embs = self.query_emb(query_ids, attention_mask_q)
+        a_embs = self.body_emb(input_ids_a, attention_mask_a)
+        b_embs = self.body_emb(input_ids_b, attention_mask_b)
+        logit_matrix = torch.stack([self._pair_logits(q_embs, a_embs, input_ids_a, attention_mask_a),
+                                    self._pair_logits(q_embs, b_embs, input_ids_b, attention_mask_b)], dim=1)  # [B, 2]
+        loss = -torch.log_softmax(logit_matrix, dim=1)[:, 0]
+        return (loss.mean(),)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -320,6 +340,15 @@ class RobertaDot_CLF_ANN_NLL_MultiChunk(RobertaDot_NLL_LN):
         emb = self._encoder(ids.device).forward(ids, None, mask)
         return emb.reshape(batchS, chunk_factor, emb.shape[-1])
 
+    def _pair_logits(self, q_embs, x_embs, input_ids_x, attention_mask_x):
+        """MaxP (models.py:87-134): best chunk of the document; a chunk whose FIRST token is padding gets -9999."""
+        batchS, full_length = input_ids_x.shape
+        chunk_factor = full_length // self.base_len
+        first = attention_mask_x.reshape(batchS, chunk_factor, -1)[:, :, 0]
+        inverted_bias = ((1 - first) * (-9999)).float()
+        scores = torch.matmul(q_embs.unsqueeze(1), x_embs.transpose(1, 2))[:, 0, :]   # [B, chunks]
+        return (scores + inverted_bias).max(dim=-1).values
+
     def encode_lens_multi_chunk(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor) -> torch.Tensor:
         """[B, full] ids + document lengths -> [B, chunks, 768]; chunk c sees max(0, min(512, len - 512c)) tokens."""
         B, full = ids_i32.shape
@@ -377,6 +406,18 @@ class BiEncoder(_B200Encoder):
 
     def body_emb(self, input_ids, attention_mask):
         return self._emb("ctx", self.ctx_model, input_ids, attention_mask)
+
+    @torch.no_grad()
+    def forward(self, query_ids, attention_mask_q, input_ids_a=None, attention_mask_a=None, input_ids_b=None,
+                attention_mask_b=None):
+        """model/models.py:253-266 (evaluation only, no autograd): (q, a) embeddings, or `(loss,)` for triplets."""
+        q_embs = self.query_emb(query_ids, attention_mask_q)
+        a_embs = self.body_emb(input_ids_a, attention_mask_a)
+        if input_ids_b is None:
+            return (q_embs, a_embs)
+        b_embs = self.body_emb(input_ids_b, attention_mask_b)
+        logit_matrix = torch.stack([(q_embs * a_embs).sum(-1), (q_embs * b_embs).sum(-1)], dim=1)
+        return ((-torch.log_softmax(logit_matrix, dim=1)[:, 0]).mean(),)
 
 
 class SEEDEncoderDot_NLL_LN(nn.Module):

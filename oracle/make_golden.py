@@ -177,6 +177,83 @@ def golden_io():
         json.dump(out, f)
 
 
+def golden_trainer_records():
+    """data/msmarco_data.py:306-362 (the trainer's consumers of ann_training_data_N) on tiny caches."""
+    from utils.util import EmbeddingCache, StreamingDataset
+    from data.msmarco_data import GetTrainingDataProcessingFn, GetTripletTrainingDataProcessingFn
+
+    rng = np.random.default_rng(7)
+    n_p, n_q, Lp, Lq = 23, 6, 12, 8
+    plens, qlens = rng.integers(1, Lp + 1, size=n_p), rng.integers(1, Lq + 1, size=n_q)
+    pids, qids = make_ids(rng, n_p, Lp, plens, 1, 500), make_ids(rng, n_q, Lq, qlens, 1, 500)
+    lines = []
+    for q in (4, 0, 5, 2, 1):
+        cand = rng.permutation(n_p)[:4].tolist()
+        lines.append(f"{q}\t{cand[0]}\t{','.join(map(str, cand[1:]))}\n")
+    out = {"n_p": n_p, "n_q": n_q, "Lp": Lp, "Lq": Lq, "plens": plens.tolist(), "qlens": qlens.tolist(),
+           "pids": pids.tolist(), "qids": qids.tolist(), "lines": lines}
+    with tempfile.TemporaryDirectory() as td:
+        refresh_oracle.write_cache(os.path.join(td, "passages"), plens, pids)
+        refresh_oracle.write_cache(os.path.join(td, "train-query"), qlens, qids)
+        args = argparse.Namespace(max_seq_length=Lp, max_query_length=Lq)
+        with EmbeddingCache(os.path.join(td, "train-query")) as qc, EmbeddingCache(os.path.join(td, "passages")) as pc:
+            for name, mk in (("pairs", GetTrainingDataProcessingFn), ("triplets", GetTripletTrainingDataProcessingFn)):
+                recs = list(StreamingDataset(lines, mk(args, qc, pc)))
+                out[name] = [[t.int().tolist() if t.dim() else int(t) for t in r] for r in recs]
+                out[name + "_dtypes"] = [str(t.dtype) for t in recs[0]]
+    with open(os.path.join(GOLD, "trainer_records.json"), "w") as f:
+        json.dump(out, f)
+
+
+def golden_trainer_losses():
+    """model/models.py:58-134,253-266: the reference's own forward() on triplets built from the encoder fixtures."""
+    from transformers import BertConfig, RobertaConfig
+    import model.models as M
+
+    out = {}
+    g = np.load(os.path.join(GOLD, "encoder_rdot_nll.npz"))
+    sd = random_roberta_state_dict(seed=0)
+    cfg = RobertaConfig(vocab_size=50265, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                        intermediate_size=3072, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5,
+                        pad_token_id=1, bos_token_id=0, eos_token_id=2, num_labels=2, return_dict=False,
+                        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    T = lambda a: torch.from_numpy(np.asarray(a)).long()   # noqa: E731
+    ids, lens, qids, qlens = g["ids"], g["lens"], g["qids"], g["qlens"]
+    mask = (np.arange(128)[None, :] < lens[:, None])
+    qmask = (np.arange(64)[None, :] < qlens[:, None])
+    ref = M.RobertaDot_NLL_LN(cfg).eval()
+    ref.load_state_dict(sd, strict=False)
+    with torch.no_grad():   # triplet i = (query i, passage i, passage 4 + i)
+        out["rdot_nll_loss"] = float(ref(T(qids), T(qmask), T(ids[:4]), T(mask[:4]), T(ids[4:]), T(mask[4:]))[0])
+        out["rdot_nll_query_passthrough_ok"] = bool(torch.equal(ref(T(qids), T(qmask)), ref.query_emb(T(qids), T(qmask))))
+    gm = np.load(os.path.join(GOLD, "encoder_multi_chunk.npz"))
+    dids, dlens = gm["ids"], gm["lens"]
+    dmask = (np.arange(2048)[None, :] < dlens[:, None])
+    refm = M.RobertaDot_CLF_ANN_NLL_MultiChunk(cfg).eval()
+    refm.load_state_dict(sd, strict=False)
+    with torch.no_grad():   # two triplets: (q0, d0, d1), (q1, d1, d0); d1 has two all-padding chunks (MaxP bias -9999)
+        out["multi_chunk_loss"] = float(refm(T(qids[:2]), T(qmask[:2]), T(dids), T(dmask), T(dids[::-1].copy()),
+                                             T(dmask[::-1].copy()))[0])
+    gd = np.load(os.path.join(GOLD, "encoder_dpr.npz"))
+    pids = gd["ids"]
+    bcfg = BertConfig(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                      intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
+                      pad_token_id=0, return_dict=False, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sdd = {**random_roberta_state_dict(seed=1, vocab=30522, max_pos=512, head=False, prefix="question_model."),
+           **random_roberta_state_dict(seed=2, vocab=30522, max_pos=512, head=False, prefix="ctx_model.")}
+    be = M.BiEncoder.__new__(M.BiEncoder)
+    torch.nn.Module.__init__(be)
+    be.question_model, be.ctx_model = M.HFBertEncoder(bcfg), M.HFBertEncoder(bcfg)
+    be.load_state_dict(sdd, strict=False)
+    be.eval()
+    pm = pids != 0
+    with torch.no_grad():   # (question = passage rows 0-1 through the question tower, ctx a = rows 0-1, ctx b = rows 2-3)
+        out["dpr_loss"] = float(be(T(pids[:2]), T(pm[:2]), T(pids[:2]), T(pm[:2]), T(pids[2:]), T(pm[2:]))[0])
+    print("trainer losses:", out)
+    with open(os.path.join(GOLD, "trainer_losses.json"), "w") as f:
+        json.dump(out, f)
+
+
 def golden_postprocess():
     """Run the reference's generate_new_ann with the third-party pieces stubbed."""
     sys.modules["transformers"].__dict__.setdefault("AdamW", torch.optim.AdamW)
@@ -339,6 +416,8 @@ if __name__ == "__main__":
     golden_io()
     golden_postprocess()
     golden_dpr()
+    golden_trainer_records()
     if "--no-encoders" not in sys.argv:
         golden_encoders()
+        golden_trainer_losses()
     print("golden fixtures written to", GOLD)

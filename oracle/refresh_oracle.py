@@ -289,3 +289,64 @@ def dpr_validate(passages, answers, I, query_embedding2id, passage_embedding2id)
             for j in range(best, n_docs):
                 hits[j] += 1
     return [v / I.shape[0] for v in hits]
+
+
+# ======================================================================================================
+# Trainer side of the refresh protocol (SURVEY.md par. 8(f) row 3): the consumers of ann_training_data_N
+# ======================================================================================================
+def parse_ann_line(line: str) -> Tuple[int, int, List[int]]:
+    """data/msmarco_data.py:308-312 / 339-343."""
+    a = line.split("\t")
+    return int(a[0]), int(a[1]), [int(x) for x in a[2].split(",")]
+
+
+def _padded(length: int, ids: np.ndarray, max_len: int, query: bool):
+    """One record the way data/msmarco_data.py:275-303 presents it: ids as stored, mask 1 for the first `length`
+    positions, token types 0 (query) / 1 (passage) on those positions."""
+    pad = max(0, max_len - int(length))
+    mask = [1] * int(length) + [0] * pad
+    types = ([0] if query else [1]) * int(length) + [0] * pad
+    return [int(x) for x in ids], mask, types
+
+
+def training_pairs(lines, qlens, qids, plens, pids, max_query_length: int, max_seq_length: int):
+    """data/msmarco_data.py:306-334: per negative a (query, positive, 1) and a (query, negative, 0) record."""
+    out = []
+    for line in lines:
+        q, pos, negs = parse_ann_line(line)
+        qr = _padded(qlens[q], qids[q], max_query_length, True)
+        pr = _padded(plens[pos], pids[pos], max_seq_length, False)
+        for n in negs:
+            nr = _padded(plens[n], pids[n], max_seq_length, False)
+            out.append([*qr, *pr, 1])
+            out.append([*qr, *nr, 0])
+    return out
+
+
+def training_triplets(lines, qlens, qids, plens, pids, max_query_length: int, max_seq_length: int):
+    """data/msmarco_data.py:337-362: per negative one (query, positive, negative) record."""
+    out = []
+    for line in lines:
+        q, pos, negs = parse_ann_line(line)
+        qr = _padded(qlens[q], qids[q], max_query_length, True)
+        pr = _padded(plens[pos], pids[pos], max_seq_length, False)
+        for n in negs:
+            out.append([*qr, *pr, *_padded(plens[n], pids[n], max_seq_length, False)])
+    return out
+
+
+def nll_triplet_loss(logits_pos: np.ndarray, logits_neg: np.ndarray) -> float:
+    """model/models.py:79-84: mean over the batch of -log_softmax([s+, s-])[0] = softplus(s- - s+)."""
+    d = np.asarray(logits_neg, dtype=np.float64) - np.asarray(logits_pos, dtype=np.float64)
+    return float(np.mean(np.maximum(d, 0.0) + np.log1p(np.exp(-np.abs(d)))))
+
+
+def dot_logits(q: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """model/models.py:79-80: (q * x).sum(-1)."""
+    return (np.asarray(q, dtype=np.float64) * np.asarray(x, dtype=np.float64)).sum(-1)
+
+
+def maxp_logits(q: np.ndarray, x_chunks: np.ndarray, first_token_mask: np.ndarray) -> np.ndarray:
+    """model/models.py:108-130: best chunk score; a chunk whose first token is padding is pushed down by 9999."""
+    s = np.einsum("bd,bcd->bc", np.asarray(q, dtype=np.float64), np.asarray(x_chunks, dtype=np.float64))
+    return (s + (1 - np.asarray(first_token_mask, dtype=np.float64)) * -9999.0).max(-1)
