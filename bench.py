@@ -205,7 +205,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=dev)
     pb, qb = args.passages_per_step, args.queries_per_step
 
     model = RobertaDot_NLL_LN(roberta_cfg())
@@ -393,4 +393,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        import torch.distributed as _dist
+        if _dist.is_available() and _dist.is_initialized():
+            _dist.destroy_process_group()
