@@ -205,7 +205,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl")
     pb, qb = args.passages_per_step, args.queries_per_step
 
     model = RobertaDot_NLL_LN(roberta_cfg())
