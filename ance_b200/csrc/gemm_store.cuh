@@ -1,4 +1,4 @@
-// gemm_store.cuh — "store" epilogue of the tcgen05 GEMM: bias, exact-erf GELU, residual add, bf16
+// gemm_store.cuh — "store" epilogue of the tcgen05 GEMM: bias, erf-GELU (two closed forms, see gelu_erf2 / gelu_logistic2), residual add, bf16
 // output through shared memory + TMA store (or fp32 output by direct stores).  Covers the encoder's
 // linear layers K2/K4/K5/K6/K7 of SURVEY.md §2.3 (HF RobertaSelfAttention / RobertaSelfOutput /
 // RobertaIntermediate / RobertaOutput reached from model/models.py:150-151, and embeddingHead,
@@ -71,6 +71,26 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   unpack2(fma2(mul2(ax, pack2(-0.5f, -0.5f)), r, relu), x0, x1);
 }
 
+// The same function in logistic form:  gelu(x) = x * Phi(x) = x / (1 + exp(-g(x))),  g = logit(Phi) fitted by an odd
+// degree-9 polynomial (minimax on the GELU itself over |x| <= 8; the leading coefficient is positive, so g -> +-inf
+// and the form saturates correctly for any |x|).  |error| <= 3.7e-6 absolute in fp32 (bf16 rounds the result at 2^-9
+// relative).  Per PAIR: 8 packed fp32 ops + 2 MUFU.EX2 + 2 MUFU.RCP  (gelu_erf2: 14 packed + 2 LOP + 2 MUFU.RCP).
+__device__ __forceinline__ void gelu_logistic2(float& x0, float& x1) {
+  const uint64_t x = pack2(x0, x1);
+  const uint64_t t = mul2(x, x);
+  // -log2(e) * (c0 + c1 t + c2 t^2 + c3 t^3 + c4 t^4)
+  uint64_t p = fma2(pack2(-3.290565928e-06f, -3.290565928e-06f), t, pack2(8.930850163e-05f, 8.930850163e-05f));
+  p = fma2(p, t, pack2(3.548454260e-04f, 3.548454260e-04f));
+  p = fma2(p, t, pack2(-1.052178442e-01f, -1.052178442e-01f));
+  p = fma2(p, t, pack2(-2.302048445e+00f, -2.302048445e+00f));
+  float g0, g1;
+  unpack2(mul2(p, x), g0, g1);
+  const uint64_t d = fma2(pack2(ex2_approx(g0), ex2_approx(g1)), pack2(1.0f, 1.0f), pack2(1.0f, 1.0f));   // 1 + exp(-g)
+  float d0, d1;
+  unpack2(d, d0, d1);
+  unpack2(mul2(x, pack2(rcp_approx(d0), rcp_approx(d1))), x0, x1);
+}
+
 template <int BN, int EPI_WARPS>
 struct EpStore {
   static constexpr uint64_t kHintA = tc05::kEvictNormal;
@@ -89,7 +109,7 @@ struct EpStore {
     const float* bias;       // [N] or null
     const __nv_bfloat16* R;  // residual [M, ldr] or null
     int ldc, ldc32, ldr;
-    int act;                 // 0 none, 1 gelu(erf)
+    int act;                 // 0 none, 1 gelu (erfc form, |err| <= 7e-7), 2 gelu (logistic form, |err| <= 3.7e-6)
   };
 
   uint32_t rphase;
@@ -131,6 +151,9 @@ struct EpStore {
     if (p.act == 1) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) gelu_erf2(f[i], f[i + 1]);
+    } else if (p.act == 2) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) gelu_logistic2(f[i], f[i + 1]);
     }
     if (direct_residual && p.R && row_ok) {
       const __nv_bfloat16* r = p.R + (size_t)row * p.ldr + col0;
