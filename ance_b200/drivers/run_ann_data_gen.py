@@ -158,6 +158,9 @@ class B200Backend:
         multi = (not is_query) and hasattr(self.model, "encode_lens_multi_chunk") and L > 512
         B = args.per_gpu_eval_batch_size
         per = max(B, (args.encode_batch_tokens // L) // B * B)  # super-batch, a multiple of the reference batch
+        bucketed = self.mask_mode != "nonzero" and not multi and getattr(args, "length_buckets", True)
+        if bucketed:
+            per *= 8   # every length bucket of a super-batch should still fill the GPU (the encoder re-splits by tokens)
         reader = StridedBatchReader(cache, per, rank=rank, world_size=W)
         outs: List[torch.Tensor] = []
         ids_out: List[np.ndarray] = []
