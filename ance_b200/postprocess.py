@@ -24,6 +24,9 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 
+_FAST_CHUNK = 16384   # queries per block of the "fast" sampler
+
+
 def _first_occurrence(pids: np.ndarray) -> np.ndarray:
     """mask[r, j] = True iff pids[r, j] does not appear in pids[r, :j]."""
     n, m = pids.shape
@@ -47,6 +50,7 @@ def generate_negatives(query_embedding2id: np.ndarray, passage_embedding2id: np.
     if nq == 0:
         return {}, 0.0, 0
     pos = np.fromiter((positives[int(q)] for q in qids), dtype=np.int64, count=nq)  # KeyError like the reference
+    p2id = np.asarray(passage_embedding2id).reshape(-1)
     if select_topk:
         sel = I[:, :negative_sample + 1]
     elif sampler == "reference":
@@ -58,15 +62,57 @@ def generate_negatives(query_embedding2id: np.ndarray, passage_embedding2id: np.
             perm[r] = p
         sel = np.take_along_axis(I, perm, axis=1)
     elif sampler == "fast":
+        # Only the head of the shuffled list is ever read (the loop stops after negative_sample valid candidates), so
+        # draw the first m positions of a uniform random permutation -- the m smallest of k i.i.d. keys, in key order --
+        # instead of shuffling all k; rows that run out of valid candidates within m fall back to a full permutation.
         rng = np.random.default_rng(seed)
-        perm = rng.permuted(np.broadcast_to(np.arange(k), (nq, k)), axis=1)
-        sel = np.take_along_axis(I, perm, axis=1)
+        m = min(k, max(negative_sample + 16, 32))
+        out: Dict[int, List[int]] = {}
+        mrr = 0.0
+        for lo in range(0, nq, _FAST_CHUNK):   # row blocks: the temporaries stay cache-sized and are reused
+            hi = min(nq, lo + _FAST_CHUNK)
+            keys = rng.random((hi - lo, k), dtype=np.float32)
+            Ic, qc, pc = I[lo:hi], qids[lo:hi], pos[lo:hi]
+            if m < k:
+                part = np.argpartition(keys, m - 1, axis=1)[:, :m]
+                head = np.take_along_axis(part, np.argsort(np.take_along_axis(keys, part, axis=1), axis=1), axis=1)
+            else:
+                head = np.argsort(keys, axis=1)
+            sel = np.take_along_axis(Ic, head, axis=1)
+            short = np.zeros(hi - lo, dtype=bool)
+            if m < k:
+                pids_h = p2id[np.where(sel < 0, 0, sel)]
+                # (<=: the reference's break needs one more valid candidate than it keeps)
+                short = ((_first_occurrence(pids_h) & (pids_h != pc[:, None])).sum(axis=1) <= negative_sample) | (sel < 0).any(axis=1)
+            if short.any():
+                rows = np.nonzero(short)[0]
+                full = np.argsort(keys[rows], axis=1)
+                o2, m2, _ = _negatives_from_selection(qc[rows], pc[rows], p2id, np.take_along_axis(Ic[rows], full, axis=1), negative_sample)
+                keep = ~short
+                o1, m1, _ = _negatives_from_selection(qc[keep], pc[keep], p2id, sel[keep], negative_sample)
+                o1.update(o2)
+                out.update((int(q), o1[int(q)]) for q in qc)
+                mrr += m1 + m2
+            else:
+                o1, m1, _ = _negatives_from_selection(qc, pc, p2id, sel, negative_sample)
+                out.update(o1)
+                mrr += m1
+        return out, mrr, nq
     else:
         raise ValueError(f"unknown sampler {sampler!r}")
+    return _negatives_from_selection(qids, pos, p2id, sel, negative_sample)
+
+
+def _negatives_from_selection(qids: np.ndarray, pos: np.ndarray, p2id: np.ndarray, sel: np.ndarray,
+                              negative_sample: int) -> Tuple[Dict[int, List[int]], float, int]:
+    """The reference's scan (run_ann_data_gen.py:357-385) over the candidate rows `sel` [nq, m] in the given order."""
+    nq = sel.shape[0]
+    if nq == 0:
+        return {}, 0.0, 0
     if (sel < 0).any():
         raise IndexError("search returned -1 labels (fewer rows than k); the reference would index "
                          "passage_embedding2id[-1] silently — refusing")
-    pids = np.asarray(passage_embedding2id).reshape(-1)[sel]
+    pids = p2id[sel]
     is_pos = pids == pos[:, None]
     valid = _first_occurrence(pids) & ~is_pos
     csum = np.cumsum(valid, axis=1)
@@ -78,9 +124,15 @@ def generate_negatives(query_embedding2id: np.ndarray, passage_embedding2id: np.
     ranks = np.arange(1, m + 1)[None, :]
     hit = is_pos & (ranks <= 10) & (np.arange(m)[None, :] < brk[:, None])
     mrr = float((hit / ranks).sum())
+    counts = take.sum(axis=1)
+    flat = pids[take]
+    if (counts == negative_sample).all():   # the common case: one reshape instead of nq boolean gathers
+        rows = flat.reshape(nq, negative_sample).tolist()
+        return dict(zip(qids.tolist(), rows)), mrr, nq
     out: Dict[int, List[int]] = {}
+    ends = np.cumsum(counts)
     for r in range(nq):
-        out[int(qids[r])] = pids[r, take[r]].tolist()
+        out[int(qids[r])] = flat[ends[r] - counts[r]:ends[r]].tolist()
     return out, mrr, nq
 
 

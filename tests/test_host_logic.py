@@ -246,3 +246,35 @@ def test_models_refuse_cpu_tensors():
     assert "roberta.encoder.layer.0.attention.self.query.weight" in keys
     with pytest.raises(AnceError):  # no CPU fallback
         m.query_emb(torch.zeros(1, 8, dtype=torch.long), torch.ones(1, 8, dtype=torch.long))
+
+
+def test_fast_sampler_head_of_permutation_and_fallback():
+    """The "fast" sampler reads only the head of a random permutation; rows whose head holds too few valid candidates
+    (MaxP: many rows per document, or the positive hit repeatedly) must fall back to the whole list."""
+    from ance_b200 import postprocess
+    rng = np.random.default_rng(0)
+    nq, k, n_rows, ns = 300, 200, 5000, 20
+    I = np.stack([rng.permutation(n_rows)[:k] for _ in range(nq)]).astype(np.int64)
+    q2id = np.arange(nq, dtype=np.int64) + 1000
+    # rows 0..99: one pid per row (plenty of candidates); rows 100..299: only 25 distinct pids among the 200 rows
+    p2id_many = np.arange(n_rows, dtype=np.int64)
+    p2id_few = (np.arange(n_rows, dtype=np.int64) % 25)
+    for p2id, lo, hi in ((p2id_many, 0, 100), (p2id_few, 100, 300)):
+        pos = {int(q2id[r]): int(p2id[I[r, 3]]) for r in range(lo, hi)}
+        negs, mrr, n = postprocess.generate_negatives(q2id[lo:hi], p2id, pos, I[lo:hi], ns, False, sampler="fast", seed=1)
+        assert n == hi - lo and list(negs.keys()) == q2id[lo:hi].tolist() and mrr >= 0.0
+        for r in range(lo, hi):
+            got = negs[int(q2id[r])]
+            cand = set(p2id[I[r]].tolist()) - {pos[int(q2id[r])]}
+            assert len(got) == min(ns, len(cand)) and len(set(got)) == len(got) and set(got) <= cand
+    # different seeds draw different negatives; the same seed is reproducible
+    pos = {int(q2id[r]): int(I[r, 0]) for r in range(100)}
+    a = postprocess.generate_negatives(q2id[:100], p2id_many, pos, I[:100], ns, False, sampler="fast", seed=5)[0]
+    b = postprocess.generate_negatives(q2id[:100], p2id_many, pos, I[:100], ns, False, sampler="fast", seed=5)[0]
+    c = postprocess.generate_negatives(q2id[:100], p2id_many, pos, I[:100], ns, False, sampler="fast", seed=6)[0]
+    assert a == b and a != c
+    # every candidate position is reachable (uniform head): over many seeds the union of picks covers the list
+    seen = set()
+    for s in range(40):
+        seen |= set(postprocess.generate_negatives(q2id[:1], p2id_many, pos, I[:1], ns, False, sampler="fast", seed=s)[0][1000])
+    assert len(seen) > 150
