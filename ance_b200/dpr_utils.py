@@ -69,18 +69,24 @@ def has_answer(answers: Sequence[str], text, tokenizer=None) -> bool:
 
 
 class AnswerMatcher:
-    """has_answer with the tokenisations cached (identical results)."""
+    """has_answer with the tokenisations cached (identical results): one refresh tests the same passage against many
+    questions, and most answers' first word does not occur in the passage at all (set test before the scan)."""
 
     def __init__(self, passages):
         self.passages = passages          # offset -> (text, title), as load_data builds it
-        self._ptok: Dict[int, List[str]] = {}
+        self._ptok: Dict[int, tuple] = {}
         self._atok: Dict[str, List[str]] = {}
 
     def _p(self, doc_id: int):
         t = self._ptok.get(doc_id)
         if t is None:
             text = self.passages[doc_id][0]
-            t = self._ptok[doc_id] = None if text is None else tokenize_uncased(text)
+            if text is None:
+                t = (None, None)
+            else:
+                words = tokenize_uncased(text)
+                t = (words, frozenset(words))
+            self._ptok[doc_id] = t
         return t
 
     def _a(self, ans: str):
@@ -90,7 +96,7 @@ class AnswerMatcher:
         return t
 
     def has_answer(self, answers: Sequence[str], doc_id: int) -> bool:
-        words = self._p(doc_id)
+        words, wset = self._p(doc_id)
         if words is None:
             return False
         for ans in answers:
@@ -99,6 +105,8 @@ class AnswerMatcher:
             if n == 0:
                 return True  # the reference's loop: an empty answer matches at i = 0 when the text is non-empty-ranged
             first = a[0]
+            if first not in wset:
+                continue
             for i in range(0, len(words) - n + 1):
                 if words[i] == first and words[i:i + n] == a:
                     return True

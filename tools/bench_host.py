@@ -88,6 +88,26 @@ def bench_merge(nq, k, shards):
     return {"queries": nq, "topk": k, "shards": shards, "seconds": dt, "queries_per_s": nq / dt, "single_thread_seconds": d1}
 
 
+def bench_answer_filter(n_q, topk, n_p):
+    """row 4: DPR answer-string filter of `validate` (run_ann_data_gen_dpr.py:281-340): n_q questions x topk passages."""
+    from ance_b200.dpr_utils import AnswerMatcher, has_answer
+    rng = np.random.default_rng(3)
+    vocab = ["w%d" % i for i in range(5000)]
+    texts = {i: (" ".join(vocab[j] for j in rng.integers(0, 5000, size=100)), "t") for i in range(n_p)}
+    answers = [[" ".join(vocab[j] for j in rng.integers(0, 5000, size=2))] for _ in range(n_q)]
+    I = rng.zipf(1.3, size=(n_q, topk)) % n_p          # popular passages are retrieved for many questions
+    m = AnswerMatcher(texts)
+    t0 = time.perf_counter()
+    hits = sum(m.has_answer(answers[q], int(I[q, j])) for q in range(n_q) for j in range(topk))
+    t_cached = time.perf_counter() - t0
+    sample = max(1, n_q // 10)
+    t0 = time.perf_counter()
+    hits_ref = sum(has_answer(answers[q], texts[int(I[q, j])][0]) for q in range(sample) for j in range(topk))
+    t_ref = (time.perf_counter() - t0) * n_q / sample
+    return {"questions": n_q, "topk": topk, "distinct_passages": int(len(np.unique(I))), "cached_matcher_s": t_cached,
+            "reference_style_s_extrapolated": t_ref, "speedup": t_ref / t_cached, "hits": int(hits), "hits_sample_ref": int(hits_ref)}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--nq", type=int, default=100000)
@@ -96,6 +116,7 @@ if __name__ == "__main__":
     out = {"cpu_count": os.cpu_count(),
            "row1_negatives": bench_negatives(a.nq, 200, 8841823, 2000),
            "row2_reader": bench_reader(a.records, 128, 20000)}
+    out["row4_dpr_answer_filter"] = bench_answer_filter(3610, 100, 200000)
     try:
         out["merge_8_shards"] = bench_merge(a.nq, 200, 8)
     except Exception as e:  # the C ABI library is needed for the merge
