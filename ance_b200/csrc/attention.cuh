@@ -10,7 +10,8 @@
 // One work item = (128-token query tile, head); a persistent CTA per SM keeps two items in flight, one per
 // softmax warpgroup (see attention_kernel).  Per 128-key block of the same sequence:
 //   S = Q K^T          tcgen05.mma  M128 N128 K16 x4   (Q, K: TMA boxes of the [tokens, 3H] QKV buffer)
-//   online softmax     4 warps, thread = query row: two passes over S in TMEM (max, then exp2),
+//   softmax            4 warps per group, thread = query row: L <= 128 one trip to TMEM (row in registers: max, exp2),
+//                      L > 128 two passes per block with online rescaling;
 //                      P written as bf16 into shared memory in the K-major SWIZZLE_128B layout
 //   O_blk = P V        tcgen05.mma  M128 N64 K16 x8    (V is the MN-major B operand)
 //   o = o*alpha + O_blk in registers; after the last block ctx = o / l  (bf16)
