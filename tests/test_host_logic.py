@@ -278,3 +278,28 @@ def test_fast_sampler_head_of_permutation_and_fallback():
     for s in range(40):
         seen |= set(postprocess.generate_negatives(q2id[:1], p2id_many, pos, I[:1], ns, False, sampler="fast", seed=s)[0][1000])
     assert len(seen) > 150
+
+
+def test_postprocess_equals_oracle_property():
+    """Random shapes of the negative-sampling scan (duplicated pids as in MaxP, the positive anywhere or absent, k smaller
+    than the request): the vectorised scan must reproduce the reference loop exactly -- negatives, their order, MRR."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(seed=st.integers(0, 2 ** 31 - 1), nq=st.integers(1, 9), k=st.integers(1, 40), n_docs=st.integers(2, 30),
+           chunks=st.sampled_from([1, 1, 4]), ns=st.integers(1, 12), topk=st.booleans())
+    def run(seed, nq, k, n_docs, chunks, ns, topk):
+        rng = np.random.default_rng(seed)
+        n_rows = n_docs * chunks
+        k2 = min(k, n_rows)
+        I = np.stack([rng.permutation(n_rows)[:k2] for _ in range(nq)]).astype(np.int64)
+        p2id = np.repeat(np.arange(n_docs, dtype=np.int64), chunks)[rng.permutation(n_rows)] if chunks > 1 \
+            else rng.permutation(n_docs).astype(np.int64)
+        q2id = rng.permutation(1000)[:nq].astype(np.int64)
+        pos = {int(q): int(rng.integers(0, n_docs)) for q in q2id}
+        random.seed(seed)
+        got = postprocess.generate_negatives(q2id, p2id, pos, I, ns, select_topk=topk, sampler="reference")
+        want = refresh_oracle.generate_negatives(q2id, p2id, pos, I, set(q2id.tolist()), ns, topk, random.Random(seed))
+        assert got[0] == want[0] and got[2] == want[2] and got[1] == pytest.approx(want[1], abs=1e-12)
+
+    run()
