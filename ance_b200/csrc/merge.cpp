@@ -18,32 +18,41 @@ namespace {
 
 void merge_range(const float* const* D, const int64_t* const* I, int n_shards, int64_t q0, int64_t q1, int k,
                  float* D_out, int64_t* I_out) {
+  // heads of the shard lists are kept in small local arrays; only the winner's head is refilled per output
   std::vector<int> pos(n_shards);
+  std::vector<float> hs(n_shards);
+  std::vector<int64_t> hi(n_shards);
+  auto refill = [&](int s, size_t base) {
+    int p = pos[s];
+    while (p < k && I[s][base + p] < 0) ++p;  // skip padding
+    pos[s] = p;
+    if (p < k) {
+      hs[s] = D[s][base + p];
+      hi[s] = I[s][base + p];
+    } else {
+      hi[s] = -1;  // exhausted
+    }
+  };
   for (int64_t q = q0; q < q1; ++q) {
-    std::fill(pos.begin(), pos.end(), 0);
     const size_t base = static_cast<size_t>(q) * k;
+    for (int s = 0; s < n_shards; ++s) {
+      pos[s] = 0;
+      refill(s, base);
+    }
     for (int o = 0; o < k; ++o) {
       int best = -1;
-      float bs = 0.f;
-      int64_t bi = 0;
       for (int s = 0; s < n_shards; ++s) {
-        while (pos[s] < k && I[s][base + pos[s]] < 0) ++pos[s];  // skip padding
-        if (pos[s] >= k) continue;
-        const float sc = D[s][base + pos[s]];
-        const int64_t id = I[s][base + pos[s]];
-        if (best < 0 || sc > bs || (sc == bs && id < bi)) {
-          best = s;
-          bs = sc;
-          bi = id;
-        }
+        if (hi[s] < 0) continue;
+        if (best < 0 || hs[s] > hs[best] || (hs[s] == hs[best] && hi[s] < hi[best])) best = s;
       }
       if (best < 0) {
         D_out[base + o] = -FLT_MAX;
         I_out[base + o] = -1;
       } else {
-        D_out[base + o] = bs;
-        I_out[base + o] = bi;
+        D_out[base + o] = hs[best];
+        I_out[base + o] = hi[best];
         ++pos[best];
+        refill(best, base);
       }
     }
   }
