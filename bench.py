@@ -142,6 +142,8 @@ def cpu_step_sample(threads, n_p=32, n_q=16, search_q=64, search_rows=262144):
 # `--impl reference` (K + W steps must end within a few minutes)
 CPU_BASELINE_SAMPLE = dict(n_p=192, n_q=48, search_q=128, search_rows=524288)
 REF_STEP_SAMPLE = dict(n_p=96, n_q=24, search_q=64, search_rows=524288)
+if os.environ.get("ANCE_BENCH_TINY_CPU"):   # contract tests only (tests/test_bench_contract.py)
+    CPU_BASELINE_SAMPLE = REF_STEP_SAMPLE = dict(n_p=2, n_q=2, search_q=4, search_rows=4096)
 
 
 def sample_text(sm):
