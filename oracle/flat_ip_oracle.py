@@ -133,3 +133,25 @@ def merge_shards(Ds, Is, k: int):
         Do[r, :order.shape[0]] = d[order]
         Io[r, :order.shape[0]] = i[order]
     return Do, Io
+
+
+def search_c(P: np.ndarray, Q: np.ndarray, k: int):
+    """The C restatement (oracle/flat_ip_oracle.c, built by ance_b200.build.build_oracle): plain loops, fp64
+    accumulation, heap selection.  Independent of BLAS and of numpy's sort; agrees with search_bruteforce()."""
+    import ctypes as C
+    import os
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liboracle.so")
+    if not os.path.exists(so):
+        from ance_b200.build import build_oracle   # compiling the checker is not using it in the product
+        build_oracle()
+    lib = C.CDLL(so)
+    lib.flat_ip_search_exact.restype = C.c_int
+    lib.flat_ip_search_exact.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    P = np.ascontiguousarray(P, dtype=np.float32)
+    Q = np.ascontiguousarray(Q, dtype=np.float32)
+    nq, dim = Q.shape[0], (Q.shape[1] if Q.ndim == 2 else P.shape[1])
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    if lib.flat_ip_search_exact(P.ctypes.data, P.shape[0], Q.ctypes.data, nq, dim, k, D.ctypes.data, I.ctypes.data) != 0:
+        raise MemoryError("flat_ip_search_exact: allocation failed")
+    return D, I

@@ -164,3 +164,34 @@ def test_encoder_oracle_dpr_golden(golden_dir):
     ids = torch.from_numpy(g["ids"])
     assert np.abs(orc.body_emb(ids, ids != 0).numpy() - g["body_emb"]).max() < 2e-4
     assert np.abs(orc.query_emb(ids, ids != 0).numpy() - g["query_emb"]).max() < 2e-4
+
+
+def test_c_restatement_agrees_with_numpy_oracle(golden_dir):
+    """Two independent restatements of the search contract (BLAS + numpy sort vs plain C loops + heap) agree bit for
+    bit: on the committed known-answer fixture, with exact duplicates (ties by row), with fewer rows than k, and on a
+    case too large for the numpy brute force's fp64 score matrix to be convenient."""
+    g = np.load(os.path.join(golden_dir, "search_kat.npz"))
+    rng = np.random.default_rng(int(g["seed"]))
+    P = rng.standard_normal((3000, 64)).astype(np.float32)
+    P[1500:1510] = P[10:20]
+    Q = rng.standard_normal((16, 64)).astype(np.float32)
+    Q[0] = P[12] * 2
+    D, I = flat_ip_oracle.search_c(P, Q, 20)
+    assert (I == g["I"]).all() and (D == g["D"]).all()
+    rng = np.random.default_rng(99)
+    P = rng.standard_normal((5000, 768)).astype(np.float32)
+    P[2500:2600] = P[:100]
+    Q = rng.standard_normal((40, 768)).astype(np.float32)
+    for k in (1, 7, 200):
+        Dc, Ic = flat_ip_oracle.search_c(P, Q, k)
+        Db, Ib = flat_ip_oracle.search_bruteforce(P, Q, k)
+        assert (Ic == Ib).all() and (Dc == Db).all()
+    Dc, Ic = flat_ip_oracle.search_c(P[:5], Q, 9)
+    Db, Ib = flat_ip_oracle.search_bruteforce(P[:5], Q, 9)
+    assert (Ic == Ib).all() and (Dc == Db).all() and (Ic[:, 5:] == -1).all()
+    De, Ie = flat_ip_oracle.search_c(P[:0], Q, 3)
+    assert (Ie == -1).all() and (De == flat_ip_oracle.LOWEST).all()
+    P = rng.standard_normal((120000, 768)).astype(np.float32)
+    Dc, Ic = flat_ip_oracle.search_c(P, Q[:8], 100)
+    Ds, Is = flat_ip_oracle.search(P, Q[:8], 100)          # the blocked sgemm + canonical rescoring oracle
+    assert (Ic == Is).all() and (Dc == Ds).all()
