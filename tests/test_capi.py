@@ -80,3 +80,42 @@ def test_merge_topk_host_padding_and_errors():
     assert Im.tolist() == [[5, 9, -1]] and Dm[0, 2] == np.finfo(np.float32).min
     with pytest.raises(ValueError):
         merge_topk_host(D, I, 4)
+
+
+def test_header_is_plain_c99_and_links_against_the_library(tmp_path):
+    """include/ance_b200.h is the drop-in boundary: it must compile as C (not only C++), and a C program using it must
+    link against libance_b200.so and run its host-only entry points without a GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from ance_b200 import _lib
+    _lib.load()
+    lib_dir = os.path.join(root, "ance_b200", "lib")
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "ance_b200.h"
+int main(void) {
+  /* host-only entry points: version string, error text of a rejected call, the k-way merge */
+  float d0[2] = {3.f, 1.f}, d1[2] = {2.f, 2.f}, out_d[2];
+  int64_t i0[2] = {10, 11}, i1[2] = {5, 20}, out_i[2];
+  const float* D[2] = {d0, d1};
+  const int64_t* I[2] = {i0, i1};
+  if (ance_merge_topk_host(D, I, 2, 1, 2, out_d, out_i, 1) != 0) return 1;
+  if (out_i[0] != 10 || out_i[1] != 5 || out_d[1] != 2.f) return 2;   /* top-2 = (3.0, row 10), (2.0, row 5): equal scores go by the smaller row */
+  if (ance_merge_topk_host(0, I, 2, 1, 2, out_d, out_i, 1) == 0) return 3;
+  if (strlen(ance_last_error()) == 0) return 4;
+  printf("%s\n", ance_version());
+  return 0;
+}
+''')
+    exe = tmp_path / "t"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                        str(src), "-o", str(exe), "-L", lib_dir, "-lance_b200", "-Wl,-rpath," + lib_dir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip(), (r.returncode, r.stdout, r.stderr)
