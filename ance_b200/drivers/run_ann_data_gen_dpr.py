@@ -160,16 +160,16 @@ def generate_new_ann(args, output_num, checkpoint_path, preloaded_data, latest_s
     path = os.path.join(args.output_dir, "ann_training_data_" + str(output_num))
     order = list(range(I.shape[0]))
     random.shuffle(order)  # the reference's unseeded module-level `random` (run_ann_data_gen_dpr.py:266-267)
-    with open(path + ".tmp", "w") as f:
+    tmp = postprocess.staging_path(path)   # never named `ann_ndcg_*` / `ann_training_data_*`: the trainer polls this dir
+    with open(tmp, "w") as f:
         for qi in order:
             qid = int(query_embedding2id[qi])
             f.write("{}\t{}\t{}\n".format(qid, train_pos_id[qid], ",".join(str(n) for n in negatives[qid])))
-    os.replace(path + ".tmp", path)
-    ndcg_path = os.path.join(args.output_dir, "ann_ndcg_" + str(output_num))
-    with open(ndcg_path + ".tmp", "w") as f:
-        json.dump({"top20": top_k_hits[19], "top100": top_k_hits[99], "top20_trivia": top_k_hits_trivia[19],
-                   "top100_trivia": top_k_hits_trivia[99], "checkpoint": checkpoint_path}, f)
-    os.replace(ndcg_path + ".tmp", ndcg_path)
+    os.replace(tmp, path)
+    postprocess.write_json_atomic(
+        os.path.join(args.output_dir, "ann_ndcg_" + str(output_num)),
+        {"top20": top_k_hits[19], "top100": top_k_hits[99], "top20_trivia": top_k_hits_trivia[19],
+         "top100_trivia": top_k_hits_trivia[99], "checkpoint": checkpoint_path})
     logger.info("dpr refresh %d done in %.1fs", output_num, time.time() - t0)
     return top_k_hits, top_k_hits_trivia
 

@@ -185,7 +185,7 @@ def write_training_data(path: str, query_embedding2id: np.ndarray, positives: Di
     else:
         order = np.random.default_rng(None if seed is None else seed + 1).permutation(len(qids)).tolist()
     n = 0
-    tmp = path + ".tmp"
+    tmp = staging_path(path)
     with open(tmp, "w") as f:
         for qi in order:
             qid = int(qids[qi])
@@ -199,9 +199,22 @@ def write_training_data(path: str, query_embedding2id: np.ndarray, positives: Di
 
 def write_ndcg(path: str, ndcg: float, checkpoint: str) -> None:
     """run_ann_data_gen.py:331-334 — written AFTER the data file."""
-    tmp = path + ".tmp"
+    write_json_atomic(path, {"ndcg": ndcg, "checkpoint": checkpoint})
+
+
+def staging_path(path: str) -> str:
+    """Temp name for an atomic write into the trainer-polled output_dir.  The unmodified trainer parses EVERY file
+    whose name starts with `ann_ndcg_` as `int(name[len('ann_ndcg_'):])` (utils/util.py:227-236, polled from
+    run_ann.py:184), so the staged file must not carry that prefix: `.tmp.<name>.<pid>` in the same directory
+    (same filesystem, so os.replace stays atomic)."""
+    d, base = os.path.split(path)
+    return os.path.join(d, ".tmp.{}.{}".format(base, os.getpid()))
+
+
+def write_json_atomic(path: str, obj) -> None:
+    tmp = staging_path(path)
     with open(tmp, "w") as f:
-        json.dump({"ndcg": ndcg, "checkpoint": checkpoint}, f)
+        json.dump(obj, f)
     os.replace(tmp, path)
 
 

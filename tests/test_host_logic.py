@@ -194,6 +194,15 @@ def test_bookkeeping(tmp_path, golden_dir):
     no, path, js = drv.get_latest_ann_data(str(out))
     assert no == 11 and path.endswith("ann_training_data_11") and js["checkpoint"] == "c11"
     assert (no, path) == refresh_oracle.latest_ann_data(str(out))[:2]
+    # a refresher killed between open() and os.replace() leaves its staged file behind: the UNMODIFIED trainer's scan
+    # (utils/util.py:227-236: int(name[len('ann_ndcg_'):]) on every file with that prefix — restated literally in
+    # refresh_oracle.latest_ann_data) must not trip over it
+    for name in ("ann_ndcg_12", "ann_training_data_12"):
+        staged = postprocess.staging_path(str(out / name))
+        assert os.path.dirname(staged) == str(out) and not os.path.basename(staged).startswith("ann_")
+        open(staged, "w").write("partial")
+    assert refresh_oracle.latest_ann_data(str(out))[:2] == (11, path)
+    assert drv.get_latest_ann_data(str(out))[:2] == (11, path)
     # checkpoints count only once scheduler.pt exists (run_ann_data_gen.py:60-63)
     tr = tmp_path / "train"
     args = argparse.Namespace(training_dir=str(tr), init_model_dir="init/")
