@@ -13,6 +13,7 @@ _LIB = None
 
 ANCE_FMT_FP16 = 0
 ANCE_FMT_BF16 = 1
+ANCE_ERR_UNSUPPORTED = 4
 ANCE_ARCH_ROBERTA = 0
 ANCE_ARCH_BERT = 1
 
@@ -36,7 +37,7 @@ class SearchStats(C.Structure):
 class EncoderConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in
                 ("arch", "n_layer", "hidden", "heads", "ffn", "vocab", "max_pos", "type_vocab", "pad_id")] + [
-        ("ln_eps", C.c_float), ("has_head", C.c_int)]
+        ("ln_eps", C.c_float), ("has_head", C.c_int), ("operand_fmt", C.c_int)]
 
 
 _FP = C.POINTER(C.c_float)
@@ -59,6 +60,7 @@ SIGNATURES = {
     "ance_last_error": (C.c_char_p, []),
     "ance_launch_count": (C.c_int64, []),
     "ance_index_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
+    "ance_index_create_over": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ance_index_destroy": (C.c_int, [C.c_void_p]),
     "ance_index_reset": (C.c_int, [C.c_void_p]),
     "ance_index_ntotal": (C.c_int64, [C.c_void_p]),

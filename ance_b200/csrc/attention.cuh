@@ -12,12 +12,13 @@
 //   S = Q K^T          tcgen05.mma  M128 N128 K16 x4   (Q, K: TMA boxes of the [tokens, 3H] QKV buffer)
 //   softmax            4 warps per group, thread = query row: L <= 128 one trip to TMEM (row in registers: max, exp2),
 //                      L > 128 two passes per block with online rescaling;
-//                      P written as bf16 into shared memory in the K-major SWIZZLE_128B layout
+//                      P written as 16-bit (FMT) into shared memory in the K-major SWIZZLE_128B layout
 //   O_blk = P V        tcgen05.mma  M128 N64 K16 x8    (V is the MN-major B operand)
-//   o = o*alpha + O_blk in registers; after the last block ctx = o / l  (bf16)
+//   o = o*alpha + O_blk in registers; after the last block ctx = o / l  (16-bit)
 // Sequence lengths: a multiple of 128, or a divisor of 128 (then a tile holds 128/L sequences and
 // cross-sequence scores are excluded).  head_dim is fixed at 64 (BERT/RoBERTa-base).
 #pragma once
+#include "act16.cuh"
 #include "tc05.cuh"
 
 namespace attn {
@@ -45,10 +46,10 @@ struct Params {
 struct Smem {
   static constexpr int kGroups = 2;                            // softmax warpgroups, each with its own Q / S / P / O
   static constexpr int kStages = 4;                            // (K, V) stages shared by both groups
-  static constexpr int kTileBytes = kTile * kDh * 2;           // 16 KB: one 128 x 64 bf16 operand tile
+  static constexpr int kTileBytes = kTile * kDh * 2;           // 16 KB: one 128 x 64 16-bit operand tile
   static constexpr int kQ = 0;
   static constexpr int kKV = kQ + kGroups * kTileBytes;        // stage s: K at +0, V at +16 KB
-  static constexpr int kP = kKV + kStages * 2 * kTileBytes;    // per group 128 x 128 bf16 (two 64-key halves)
+  static constexpr int kP = kKV + kStages * 2 * kTileBytes;    // per group 128 x 128 16-bit (two 64-key halves)
   static constexpr int kBias = kP + kGroups * kTile * kTile * 2;   // per group 128 floats + 4 ballots
   static constexpr int kBiasStride = kTile * 4 + 16;
   static constexpr int kBar = kBias + kGroups * kBiasStride;
@@ -71,7 +72,8 @@ constexpr int kThreads = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 
 // (a,0) (b,0) (a,1) (b,1) ... for the item pair (a, b); producer, MMA issuer and both groups derive that order
 // from the same loop nest.
 // kPacked: L < 128, a tile holds 128/L sequences.  kSingle: L <= 128, one key block per item.
-template <bool kPacked, bool kSingle>
+// FMT: 16-bit format of Q / K / V, of the probabilities P and of the output (act16.cuh).
+template <bool kPacked, bool kSingle, uint32_t FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmCTX, const Params p) {
   static_assert(kSingle || !kPacked, "a packed tile has a single key block");
@@ -148,8 +150,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   } else if (warp == 1) {
     // ================================= MMA issuer =================================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_f16(kTile, kTile, kFmtBF16, 0, 0);  // Q K^T : both K-major
-      constexpr uint32_t idesc_o = make_idesc_f16(kTile, kDh, kFmtBF16, 0, 1);    // P V   : V is MN-major
+      constexpr uint32_t idesc_s = make_idesc_f16(kTile, kTile, FMT, 0, 0);  // Q K^T : both K-major
+      constexpr uint32_t idesc_o = make_idesc_f16(kTile, kDh, FMT, 0, 1);    // P V   : V is MN-major
       Ring<Smem::kStages> kv;
       uint32_t qc[2] = {0, 0}, bc[2] = {0, 0};
       int prev_g = -1, prev_stage = 0;   // block whose S is issued and whose P V is still owed
@@ -318,8 +320,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 const float p0 = ex2_ftz(fmaf(__uint_as_float(v[c + i]), sc, nm));
                 const float p1 = ex2_ftz(fmaf(__uint_as_float(v[c + i + 1]), sc, nm));
                 rs[(i >> 1) & 3] += p0 + p1;
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-                pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                pk[i >> 1] = act16::Act<FMT>::pack2(p0, p1);
               }
             }
             store_chunks(sP + (c >> 6) * (kTile * 128) + row * 128, (c & 63) >> 3, pk);
@@ -353,7 +354,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           if (plain) m_blk *= p.scale_log2;
           m_new = fmaxf(m_run, m_blk);
           alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
-          // pass 2: p = exp2(t - m_new), row sum, bf16 P into swizzled smem
+          // pass 2: p = exp2(t - m_new), row sum, 16-bit P into swizzled smem
           rsum = 0.f;
 #pragma unroll 1
           for (int c = 0; c < kTile; c += 32) {
@@ -373,8 +374,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                   const float p0 = ex2_ftz(fmaf(__uint_as_float(v[i]), p.scale_log2, nm));
                   const float p1 = ex2_ftz(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, nm));
                   rsum += p0 + p1;
-                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-                  pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                  pk[i >> 1] = act16::Act<FMT>::pack2(p0, p1);
                 }
               } else {
 #pragma unroll
@@ -383,8 +383,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                   const float t1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, sbias[c + i + 1]);
                   const float p0 = ex2_ftz(t0 + nm), p1 = ex2_ftz(t1 + nm);
                   rsum += p0 + p1;
-                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-                  pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                  pk[i >> 1] = act16::Act<FMT>::pack2(p0, p1);
                 }
               }
             }
@@ -416,7 +415,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           }
         }
       }
-      // ctx tile = o / l as bf16: staged in this group's P buffer (the PV MMA has finished reading it), one TMA store
+      // ctx tile = o / l in 16 bits: staged in this group's P buffer (the PV MMA has finished reading it), one TMA store
       {
         const float inv = 1.0f / l_run;
         if constexpr (kSingle) {
@@ -433,8 +432,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[c + i] * inv, o[c + i + 1] * inv);
-            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            pk[i >> 1] = act16::Act<FMT>::pack2(o[c + i] * inv, o[c + i + 1] * inv);
           }
           store_chunks(sP + row * 128, c >> 3, pk);
         }

@@ -103,10 +103,10 @@ int run_dbg(const void* A, const void* B, int M, int N, int K, const float* bias
     ance::set_error("cuTensorMapEncodeTiled failed for the residual (M=%d N=%d)", M, N);
     return ANCE_ERR_CUDA;
   }
-  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.C = reinterpret_cast<uint16_t*>(C);
   p.C32 = C32;
   p.bias = bias;
-  p.R = reinterpret_cast<const __nv_bfloat16*>(R);
+  p.R = reinterpret_cast<const uint16_t*>(R);
   p.ldc = N;
   p.ldc32 = N;
   p.ldr = N;

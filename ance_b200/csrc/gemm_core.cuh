@@ -35,7 +35,25 @@ struct WorkShape {
   int n_splits;          // work items per m block
   int n_blks_per_split;  // ceil(num_n_blks / n_splits)
   unsigned long long hint_a, hint_b;  // L2 cache-policy words of the A / B tile loads (0 = the epilogue's default)
+  // Soft barrier between CTA pairs that sweep the SAME B rows (search, n_splits == 1): pace[c] = progress of cluster c
+  // in tiles; a producer does not run more than pace_window tiles ahead of the slowest cluster, so that a B tile fetched
+  // from HBM by the first pair is still in L2 when the last pair asks for it.  null = off.
+  int* pace;
+  int pace_window;
 };
+
+// Publish this cluster's progress and wait (bounded: ~100 us, then go on regardless — the barrier is a bandwidth
+// optimisation, never a correctness requirement, and must not hang if the grid is not fully co-resident).
+static __device__ __noinline__ void pace_wait(int* pace, int window, int me, int n_clusters, int seq) {
+  volatile int* vp = pace;
+  vp[me] = seq;
+  const long long t0 = clock64();
+  for (;;) {
+    int mn = 0x7fffffff;
+    for (int c = 0; c < n_clusters; ++c) mn = min(mn, vp[c]);
+    if (seq - mn <= window || clock64() - t0 > 200000ll) break;
+  }
+}
 
 struct EpiCtx {
   int m_blk, split;
@@ -119,6 +137,8 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nb1 = min(nb0 + ws.n_blks_per_split, ws.num_n_blks);
         const int a_row = (m_blk * CG + (int)cta_rank) * BM;
         for (int nb = nb0; nb < nb1; ++nb) {
+          if (ws.pace != nullptr && leader && ((nb - nb0) & 7) == 0)
+            pace_wait(ws.pace, ws.pace_window, cluster_id, num_clusters, ((w - cluster_id) / num_clusters) * ws.num_n_blks + (nb - nb0));
           const int b_row = nb * BN + (int)cta_rank * Plan::kBRows;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1, 1);
@@ -140,6 +160,7 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (ws.pace != nullptr && leader) *reinterpret_cast<volatile int*>(ws.pace + cluster_id) = 0x7fffffff;   // done: never the slowest
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
@@ -219,14 +240,20 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // host-side launch helper
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs through the C ABI)
 inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 template <class Ep, int BN, int STAGES, int CG, int EPI_WARPS, uint32_t FMT>
@@ -234,11 +261,12 @@ cudaError_t launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const WorkSha
                    const typename Ep::Params& ep, int max_ctas, cudaStream_t stream) {
   using Plan = SmemPlan<BN, STAGES, CG, Ep::kSmemBytes>;
   auto kern = tc05_gemm_kernel<Ep, BN, STAGES, CG, EPI_WARPS, FMT>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};   // the opt-in is per device, not per process
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kDynamicBytes);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   const int total = ws.num_m_blks * ws.n_splits;
   int clusters = min(total, (max_ctas > 0 ? max_ctas : sm_count()) / CG);
@@ -269,6 +297,8 @@ inline WorkShape make_shape(int M, int N, int K, int BN, int CG, int n_splits /*
   ws.n_blks_per_split = (ws.num_n_blks + n_splits - 1) / n_splits;
   ws.n_splits = (ws.num_n_blks + ws.n_blks_per_split - 1) / ws.n_blks_per_split;
   ws.hint_a = ws.hint_b = 0;
+  ws.pace = nullptr;
+  ws.pace_window = 0;
   return ws;
 }
 

@@ -9,6 +9,7 @@
 // (cp.async.bulk.tensor.2d.global.shared::cta); the stores to HBM are then full 128-byte lines and run
 // asynchronously under the next slab's math.  Rows / columns past the tensor edge are clipped by TMA.
 #pragma once
+#include "act16.cuh"
 #include "gemm_core.cuh"
 
 namespace gemm {
@@ -91,8 +92,11 @@ __device__ __forceinline__ void gelu_logistic2(float& x0, float& x1) {
   unpack2(mul2(x, pack2(rcp_approx(d0), rcp_approx(d1))), x0, x1);
 }
 
-template <int BN, int EPI_WARPS>
+// FMT: 16-bit format of the OUTPUT and of the residual (act16.cuh); the operand format of the GEMM itself is the
+// FMT parameter of gemm::launch.
+template <int BN, int EPI_WARPS, uint32_t FMT = tc05::kFmtBF16>
 struct EpStore {
+  using A16 = act16::Act<FMT>;
   static constexpr uint64_t kHintA = tc05::kEvictNormal;
   static constexpr uint64_t kHintB = tc05::kEvictLast;  // weights: keep in L2
   static constexpr int kColGroups = EPI_WARPS / 4;
@@ -102,12 +106,12 @@ struct EpStore {
   static_assert(EPI_WARPS % 4 == 0 && kColsPerGroup % 64 == 0, "epilogue warp layout");
 
   struct alignas(64) Params {
-    CUtensorMap tmC;         // bf16 output [M, N], box {64, 128}, SWIZZLE_128B (valid when C != null)
-    CUtensorMap tmR;         // bf16 residual, same geometry (valid when R != null and C != null)
-    __nv_bfloat16* C;        // [M, ldc] bf16 or null
+    CUtensorMap tmC;         // 16-bit output [M, N], box {64, 128}, SWIZZLE_128B (valid when C != null)
+    CUtensorMap tmR;         // 16-bit residual, same geometry (valid when R != null and C != null)
+    uint16_t* C;             // [M, ldc] 16-bit (FMT) or null
     float* C32;              // [M, ldc32] fp32 or null (direct stores)
     const float* bias;       // [N] or null
-    const __nv_bfloat16* R;  // residual [M, ldr] or null
+    const uint16_t* R;       // residual [M, ldr] (FMT) or null
     int ldc, ldc32, ldr;
     int act;                 // 0 none, 1 gelu (erfc form, |err| <= 7e-7), 2 gelu (logistic form, |err| <= 3.7e-6)
   };
@@ -156,22 +160,22 @@ struct EpStore {
       for (int i = 0; i < 32; i += 2) gelu_logistic2(f[i], f[i + 1]);
     }
     if (direct_residual && p.R && row_ok) {
-      const __nv_bfloat16* r = p.R + (size_t)row * p.ldr + col0;
+      const uint16_t* r = p.R + (size_t)row * p.ldr + col0;
       if (full) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 q = __ldg(reinterpret_cast<const uint4*>(r) + j);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+          const uint32_t h[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 x = __bfloat1622float2(h[t]);
+            const float2 x = A16::unpack2(h[t]);
             f[j * 8 + t * 2] += x.x;
             f[j * 8 + t * 2 + 1] += x.y;
           }
         }
       } else {
         for (int i = 0; i < 32; ++i)
-          if (col0 + i < ws.N) f[i] += __bfloat162float(r[i]);
+          if (col0 + i < ws.N) f[i] += A16::to_float(r[i]);
       }
     }
   }
@@ -243,18 +247,19 @@ struct EpStore {
             uint4* cp = reinterpret_cast<uint4*>(rowp + (((h * 4 + q) ^ (r_in_tile & 7)) * 16));
             if (tma_res) {
               const uint4 rv = *cp;
-              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+              const uint32_t rh[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const float2 x = __bfloat1622float2(rh[t]);
+                const float2 x = A16::unpack2(rh[t]);
                 f[q * 8 + t * 2] += x.x;
                 f[q * 8 + t * 2 + 1] += x.y;
               }
             }
             uint4 o;
-            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) oh[t] = __floats2bfloat162_rn(f[q * 8 + t * 2], f[q * 8 + t * 2 + 1]);
+            o.x = A16::pack2(f[q * 8 + 0], f[q * 8 + 1]);
+            o.y = A16::pack2(f[q * 8 + 2], f[q * 8 + 3]);
+            o.z = A16::pack2(f[q * 8 + 4], f[q * 8 + 5]);
+            o.w = A16::pack2(f[q * 8 + 6], f[q * 8 + 7]);
             *cp = o;
           }
         }

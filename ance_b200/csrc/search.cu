@@ -13,9 +13,13 @@
 //      <= n_splits * k' candidates, sort by (score desc, row asc), emit top-k, and CERTIFY: every
 //      row that was not a candidate has coarse score <= thr, hence exact score <= thr + eps(q);
 //      if thr + eps(q) < k-th exact score the result is provably the exact top-k.
-//   4. exact_* kernels : queries that could not be certified (ties at the boundary, adversarial
-//      data) are recomputed by brute force in exact arithmetic.  Also the validation path
-//      (ance_index_search_exact).
+//   4. tier 2, for the queries step 3 could not certify: the SAME coarse kernel once more over those queries only,
+//      started from a per-query threshold t(q) = s_k - eps(q) (s_k = k-th exact score found so far, a lower bound of
+//      the true one).  Every row that can still belong to the top-k has coarse score > t(q), so unless more than
+//      ~2000 rows per split sit within eps of the boundary nothing is dropped and the result is certified BY
+//      CONSTRUCTION: a failed certificate costs one more coarse pass over the failed queries, not a brute force.
+//   5. exact_* kernels : what is left (thousands of near-ties at the boundary: duplicated rows, adversarial data) is
+//      recomputed by brute force in exact arithmetic.  Also the validation path (ance_index_search_exact).
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -74,6 +78,7 @@ template <bool kBF16>
 __global__ void quantize_rows_kernel(const float* __restrict__ X, uint16_t* __restrict__ X16, int64_t n, int d,
                                      float* __restrict__ norm_hat, float* __restrict__ norm_delta,
                                      unsigned int* __restrict__ max_stats, int* __restrict__ err_flag) {
+  // err_flag: set to 1 when a value is non-finite after rounding (fp16 overflow, or inf / NaN in the input)
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -139,10 +144,14 @@ struct EpTopK {
   struct Params {
     float* scratch_sc;  // [gridDim.x * 128 * CAP] reservoir scores
     int* scratch_id;    // [gridDim.x * 128 * CAP] reservoir rows
-    int* cand_id;       // [nq * n_splits * kprime]
+    int* cand_id;       // [nq * n_splits * out_cap]
     int* cand_cnt;      // [nq * n_splits]
-    float* cand_thr;    // [nq * n_splits]  k'-th coarse score (-inf when fewer than k' rows were seen)
-    int kprime, nq, n_rows;
+    float* cand_thr;    // [nq * n_splits]  final running threshold: every row NOT in the candidate list has coarse score <= it
+    const float* thr_init;  // [nq] starting threshold per query (tier 2), or null: -inf
+    int kprime;         // a reservoir that fills up is compacted to its best kprime entries
+    int out_cap;        // entries kept per (query, split) at the end: kprime (tier 1) or the reservoir size (tier 2: nothing
+                        // that passed the threshold is dropped unless the reservoir itself overflowed)
+    int nq, n_rows;
   };
 
   float thr;
@@ -155,7 +164,7 @@ struct EpTopK {
     const size_t base = (static_cast<size_t>(blockIdx.x) * gemm::BM + r) * CAP;
     sc = p.scratch_sc + base;
     id = p.scratch_id + base;
-    thr = (cx.row0 + r < p.nq) ? -INFINITY : INFINITY;
+    thr = (cx.row0 + r < p.nq) ? (p.thr_init ? __ldg(p.thr_init + cx.row0 + r) : -INFINITY) : INFINITY;
     cnt = 0;
   }
 
@@ -248,7 +257,7 @@ struct EpTopK {
 
   __device__ __forceinline__ void end_work(const Params& p, const gemm::WorkShape& ws, const gemm::EpiCtx& cx) {
     __syncwarp();
-    unsigned need = __ballot_sync(0xffffffffu, cnt > p.kprime);
+    unsigned need = __ballot_sync(0xffffffffu, cnt > p.out_cap);
     while (need) {
       const int src = __ffs(need) - 1;
       need &= need - 1;
@@ -261,7 +270,7 @@ struct EpTopK {
       const float t = __shfl_sync(0xffffffffu, thr, l);
       const int* s_id = shfl_ptr(id, l);
       const size_t slot = static_cast<size_t>(row) * ws.n_splits + cx.split;
-      int* out = p.cand_id + slot * p.kprime;
+      int* out = p.cand_id + slot * p.out_cap;
       for (int i = cx.lane; i < n; i += 32) out[i] = s_id[i];
       if (cx.lane == 0) {
         p.cand_cnt[slot] = n;
@@ -333,21 +342,58 @@ struct RescoreParams {
   const int* cand_id;
   const int* cand_cnt;
   const float* cand_thr;
-  int n_splits, kprime, k;
+  int n_splits, cand_stride, k;   // cand_stride = EpTopK out_cap
   const float* qn_hat;
   const float* qn_delta;
   const unsigned int* pstats;  // [0] max ||p^||, [1] max ||p - p^|| (float bits)
-  float accum_rel;             // bound on the tensor core's accumulation error / (||q^|| ||p^||)
+  float accum_rel;             // bound on the tensor core's accumulation error / (||q^|| ||p^||), see coarse_rescore_pass
   float* D;
   int64_t* I;
   int64_t row_offset;
   const int* qlist;    // block b handles candidate slot b of query qlist[b] (null: query b)
   int* flagged_list;   // uncertified queries of this pass
+  float* flagged_thr;  // starting threshold of the next tier for flagged_list[i] (null: not needed)
   int flag_slot;       // counters[flag_slot] counts them
   int* counters;       // [0] tier-1 flagged [1] n_candidates [2] max eps bits [3] tier-2 flagged
   unsigned int* max_eps;
-  int sort_n;          // pow2 >= n_splits * kprime
+  int sort_n;          // pow2 >= total candidates of a query
 };
+
+// exact <q, p_c> of kNB candidate rows at once: all the row's 16-byte loads (d / 128 per lane and row) are issued
+// before the first fp64 FMA, so a warp keeps kNB * d / 128 gathers in flight instead of one (the rows are random
+// 3 KB reads: latency, not bandwidth, bounded the one-row-at-a-time form at 0.14 of HBM).  kJ = d / 128 (768: kJ = 6).
+template <int kNB, int kJ>
+__device__ __forceinline__ void warp_dots_f64(const float* __restrict__ q_smem, const float* const (&rows)[kNB], int d,
+                                              int lane, double (&out)[kNB]) {
+  float4 b[kNB][kJ];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    {
+#pragma unroll
+      for (int c = 0; c < kNB; ++c) b[c][j] = __ldg(reinterpret_cast<const float4*>(rows[c] + j * 128 + lane * 4));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kNB; ++c) out[c] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    {
+      const float4 a = *reinterpret_cast<const float4*>(q_smem + j * 128 + lane * 4);
+#pragma unroll
+      for (int c = 0; c < kNB; ++c) {   // same association as warp_dot_f64: the result is bit-identical
+        out[c] = fma(static_cast<double>(a.x), static_cast<double>(b[c][j].x), out[c]);
+        out[c] = fma(static_cast<double>(a.y), static_cast<double>(b[c][j].y), out[c]);
+        out[c] = fma(static_cast<double>(a.z), static_cast<double>(b[c][j].z), out[c]);
+        out[c] = fma(static_cast<double>(a.w), static_cast<double>(b[c][j].w), out[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) out[c] += __shfl_xor_sync(0xffffffffu, out[c], s);
+  }
+}
 
 __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -371,13 +417,34 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   const int m = offs[p.n_splits];
   for (int i = threadIdx.x; i < p.sort_n; i += blockDim.x) keys[i] = 0ull;
   __syncthreads();
+  constexpr int kNB = 4;
+  const bool wide = p.d == 768;   // the path's dimension (models.py:145-146); other dims take the one-row loop
   for (int s = 0; s < p.n_splits; ++s) {
     const int n = offs[s + 1] - offs[s];
-    const int* ids = p.cand_id + (static_cast<size_t>(ql) * p.n_splits + s) * p.kprime;
-    for (int c = warp; c < n; c += nwarps) {
-      const int row = ids[c];
-      const double dot = warp_dot_f64(qs, p.P + static_cast<size_t>(row) * p.d, p.d, lane);
-      if (lane == 0) keys[offs[s] + c] = make_key(static_cast<float>(dot), static_cast<uint32_t>(row));
+    const int* ids = p.cand_id + (static_cast<size_t>(ql) * p.n_splits + s) * p.cand_stride;
+    if (wide) {
+      for (int c0 = warp * kNB; c0 < n; c0 += nwarps * kNB) {
+        int row[kNB];
+        const float* rp[kNB];
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) {
+          row[c] = ids[min(c0 + c, n - 1)];
+          rp[c] = p.P + static_cast<size_t>(row[c]) * p.d;
+        }
+        double dot[kNB];
+        warp_dots_f64<kNB, 6>(qs, rp, p.d, lane, dot);
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < kNB; ++c)
+            if (c0 + c < n) keys[offs[s] + c0 + c] = make_key(static_cast<float>(dot[c]), static_cast<uint32_t>(row[c]));
+        }
+      }
+    } else {
+      for (int c = warp; c < n; c += nwarps) {
+        const int row = ids[c];
+        const double dot = warp_dot_f64(qs, p.P + static_cast<size_t>(row) * p.d, p.d, lane);
+        if (lane == 0) keys[offs[s] + c] = make_key(static_cast<float>(dot), static_cast<uint32_t>(row));
+      }
     }
   }
   block_bitonic_desc(keys, p.sort_n);
@@ -391,16 +458,25 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     for (int s = 0; s < p.n_splits; ++s) thr = fmaxf(thr, p.cand_thr[static_cast<size_t>(ql) * p.n_splits + s]);
     const float maxp = __uint_as_float(p.pstats[0]), maxdp = __uint_as_float(p.pstats[1]);
     const float qn = p.qn_hat[q], qd = p.qn_delta[q];
+    // |coarse_j - <q, p_j>| <= eps for EVERY row j (Cauchy-Schwarz on the operand rounding + the accumulation bound);
+    // the factor covers the fp32 roundings of this expression itself (norms are already rounded up)
     const float eps = (qd * maxp + qn * maxdp + qd * maxdp + p.accum_rel * qn * maxp) * 1.0001f;
     bool certified;
     if (thr == -INFINITY) certified = true;       // every row of the index was a candidate
-    else if (m < p.k) certified = false;          // cannot happen (thr finite => >= k' >= k candidates)
-    else certified = (thr + eps < key_score(keys[p.k - 1]));
+    else if (m < p.k) certified = false;          // cannot happen (thr finite => >= k candidates passed it)
+    else certified = (__fadd_ru(thr, eps) < key_score(keys[p.k - 1]));
     atomicAdd(&p.counters[1], m);
     atomicMax(p.max_eps, __float_as_uint(eps));
     if (!certified) {
       const int slot = atomicAdd(&p.counters[p.flag_slot], 1);
       p.flagged_list[slot] = q;
+      if (p.flagged_thr) {
+        // Next tier starts from t < s_k - eps: every row whose exact score reaches s_k (the k-th exact score found so
+        // far, a lower bound of the final one) has coarse score >= s_k - eps > t, i.e. passes the filter.
+        const float sk = (m >= p.k) ? key_score(keys[p.k - 1]) : -INFINITY;
+        const float x = __fsub_rd(sk, eps);
+        p.flagged_thr[slot] = (sk == -INFINITY) ? -INFINITY : __fsub_rd(x, fmaxf(fabsf(sk), eps) * 1.0e-6f);
+      }
     }
   }
 }
@@ -564,30 +640,35 @@ __global__ void fill_i32(int* p, int n, int v) {
 struct ance_index {
   int dim = 0;
   int64_t cap = 0, n = 0;
-  int fmt = ANCE_FMT_BF16;
+  int fmt = ANCE_FMT_FP16;
   int device = 0;
   float* P32 = nullptr;      // [cap, dim]
+  bool owns_p32 = true;      // false: caller-owned storage (ance_index_create_over)
   uint16_t* P16 = nullptr;   // [cap, dim]
   unsigned int* pstats = nullptr;  // [2]
-  int* err_flag = nullptr;
   // tunables
-  int kprime = 0, n_splits = 0, cta_group = 2, max_ctas = 0, exact_fallback = 1, tier2 = 1;
+  int kprime = 0, n_splits = 0, cta_group = 2, max_ctas = 0, exact_fallback = 1, tier2 = 1, pace_window = 32;
   // workspace (grown lazily)
   uint16_t* Q16 = nullptr; float* qn_hat = nullptr; float* qn_delta = nullptr; int64_t q_cap = 0;
   float* scratch_sc = nullptr; int* scratch_id = nullptr; size_t scratch_elems = 0;
   int* cand_id = nullptr; int* cand_cnt = nullptr; float* cand_thr = nullptr; size_t cand_slots = 0, cand_ids = 0;
-  int* flagged = nullptr; int64_t flagged_cap = 0;
+  int* flagged = nullptr; float* flagged_thr = nullptr; int64_t flagged_cap = 0;
   int* flagged2 = nullptr; size_t flagged2_cap = 0;
   uint16_t* Q16b = nullptr; size_t q16b_elems = 0;
-  int* counters = nullptr;          // [4]: n_flagged, n_candidates, max_eps bits, spare
+  int* pace = nullptr;              // [kMaxPace] progress counters of the sweeping CTA pairs (soft barrier)
+  // [0] tier-1 flagged  [1] candidates rescored  [2] max eps bits  [3] tier-2 flagged  [4,5] spare
+  // [6] a QUERY was non-finite after rounding (cleared per search)  [7] an index ROW was (sticky until reset / requantise)
+  int* counters = nullptr;
   uint64_t* chunk_keys = nullptr; size_t chunk_keys_elems = 0;
   // last search
   ance_search_stats stats{};
   cudaStream_t last_stream = nullptr;
-  bool stats_pending = false;
 };
 
 namespace {
+
+constexpr int kMaxPace = 256;
+constexpr int kCntQueryErr = 6, kCntRowErr = 7, kNumCounters = 8;
 
 template <class T>
 int ensure(T** ptr, size_t* have, size_t want) {
@@ -620,9 +701,18 @@ int check_device() {
   return ANCE_OK;
 }
 
+// handles are bound to the device that was current at creation (header): refuse anything else instead of launching
+// on the wrong GPU
+int check_handle_device(const ance_index* ix, const char* who) {
+  int dev = -1;
+  ANCE_CUDA(cudaGetDevice(&dev));
+  ANCE_REQUIRE(dev == ix->device, "%s: the index belongs to device %d but device %d is current", who, ix->device, dev);
+  return ANCE_OK;
+}
+
 template <int BN, int STAGES, int CG, int CAP, uint32_t FMT>
-int launch_coarse(ance_index* ix, const uint16_t* Q16, int64_t nq, int kprime, int n_splits_req, int* n_splits_out,
-                  cudaStream_t st) {
+int launch_coarse(ance_index* ix, const uint16_t* Q16, int64_t nq, int kprime, int out_cap, const float* thr_init,
+                  int n_splits_req, int* n_splits_out, cudaStream_t st) {
   using Ep = EpTopK<BN, CAP>;
   const int N = static_cast<int>(ix->n);
   gemm::WorkShape ws = gemm::make_shape(static_cast<int>(nq), N, ix->dim, BN, CG, n_splits_req);
@@ -649,14 +739,26 @@ int launch_coarse(ance_index* ix, const uint16_t* Q16, int64_t nq, int kprime, i
   if ((rc = ensure(&ix->cand_cnt, &a, slots))) return rc;
   if ((rc = ensure(&ix->cand_thr, &b, slots))) return rc;
   ix->cand_slots = a;
-  if ((rc = ensure(&ix->cand_id, &ix->cand_ids, slots * kprime))) return rc;
+  if ((rc = ensure(&ix->cand_id, &ix->cand_ids, slots * out_cap))) return rc;
+  // Soft barrier between the sweeping CTA pairs (gemm_core.cuh): only when every work item sweeps the WHOLE corpus
+  // (n_splits == 1) and several pairs do so at once — then they share each corpus tile through L2 as long as they stay
+  // within `pace_window` tiles of each other.  Without it the pairs drift apart and every one of them streams the corpus
+  // from HBM by itself (ncu, round 1: 788 GB of DRAM reads for a 13.6 GB operand).
+  const int clusters = std::min(ws.num_m_blks * ws.n_splits, ctas / CG);
+  if (ws.n_splits == 1 && clusters > 1 && clusters <= kMaxPace && ix->pace_window > 0 && ws.num_n_blks > 4 * ix->pace_window) {
+    ANCE_CUDA(cudaMemsetAsync(ix->pace, 0, kMaxPace * sizeof(int), st));
+    ws.pace = ix->pace;
+    ws.pace_window = ix->pace_window;
+  }
   typename Ep::Params p;
   p.scratch_sc = ix->scratch_sc;
   p.scratch_id = ix->scratch_id;
   p.cand_id = ix->cand_id;
   p.cand_cnt = ix->cand_cnt;
   p.cand_thr = ix->cand_thr;
+  p.thr_init = thr_init;
   p.kprime = kprime;
+  p.out_cap = out_cap;
   p.nq = static_cast<int>(nq);
   p.n_rows = N;
   {
@@ -688,11 +790,8 @@ int run_exact(ance_index* ix, const float* Q, const int* qlist, int nq, int k, f
   if (rc) return rc;
   ep.chunk_keys = ix->chunk_keys;
   const size_t smem = static_cast<size_t>(kExQB) * kExBuf * 8 + static_cast<size_t>(kExQB) * ix->dim * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ANCE_CUDA(cudaFuncSetAttribute(exact_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
-  }
+  // per device and cheap: set on every call rather than behind a process-wide flag
+  ANCE_CUDA(cudaFuncSetAttribute(exact_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   for (int b0 = 0; b0 < nq; b0 += kExactBatch) {
     const int nb = std::min(kExactBatch, nq - b0);
     ep.qlist = qlist ? qlist + b0 : nullptr;
@@ -710,13 +809,18 @@ int run_exact(ance_index* ix, const float* Q, const int* qlist, int nq, int k, f
 }
 
 // One coarse pass + exact rescoring + certificate over `nq` queries whose 16-bit rows are Q16[0..nq);
-// qlist (or identity) maps them to rows of q_f32 / D / I.  Uncertified queries are appended to
-// flagged_out and counted in counters[flag_slot].
+// qlist (or identity) maps them to rows of q_f32 / D / I.  thr_init == null: tier 1 (running top-k' from -inf, k'
+// candidates per split kept).  thr_init != null: tier 2 (start from the per-query threshold, keep everything that
+// passes it).  Uncertified queries are appended to flagged_out (+ their next-tier threshold to flagged_thr_out) and
+// counted in counters[flag_slot].
 int coarse_rescore_pass(ance_index* ix, const uint16_t* Q16, const float* q_f32, int64_t nq, const int* qlist,
-                        int kprime, int n_splits_req, int k, float* D_dev, int64_t* I_dev, int64_t row_offset,
-                        int* flagged_out, int flag_slot, int* ns_out, cudaStream_t st) {
+                        int kprime, const float* thr_init, int n_splits_req, int k, float* D_dev, int64_t* I_dev,
+                        int64_t row_offset, int* flagged_out, float* flagged_thr_out, int flag_slot, int* ns_out,
+                        cudaStream_t st) {
   int rc;
   const int cap = (kprime <= 512) ? 1024 : 2048;
+  // tier 2 keeps whatever the reservoir holds at the end (at most cap - 32 entries: a fuller one is compacted at once)
+  const int out_cap = thr_init ? cap : kprime;
   const int cg = ix->cta_group;
   const int clusters = (ix->max_ctas > 0 ? ix->max_ctas : gemm::sm_count()) / cg;
   const int q_tiles = static_cast<int>((nq + gemm::BM * cg - 1) / (gemm::BM * cg));
@@ -726,7 +830,7 @@ int coarse_rescore_pass(ance_index* ix, const uint16_t* Q16, const float* q_f32,
     // split count whose work-item count fills whole waves best (ties: fewer splits = fewer candidates).
     n_splits = 1;
     if (q_tiles < 2 * clusters) {
-      const int max_splits = std::max(1, std::min(16, 4096 / kprime));
+      const int max_splits = std::max(1, std::min(16, 4096 / out_cap));
       double best = -1.0;
       for (int sp = 1; sp <= max_splits; ++sp) {
         const long items = static_cast<long>(q_tiles) * sp;
@@ -736,13 +840,13 @@ int coarse_rescore_pass(ance_index* ix, const uint16_t* Q16, const float* q_f32,
       }
     }
   }
-  while (n_splits > 1 && n_splits * kprime > 4096) --n_splits;
-  ANCE_REQUIRE(n_splits * kprime <= 4096, "ance_index_search: n_splits * kprime = %d exceeds 4096", n_splits * kprime);
+  while (n_splits > 1 && n_splits * out_cap > 4096) --n_splits;
+  ANCE_REQUIRE(n_splits * out_cap <= 4096, "ance_index_search: n_splits * candidates per split = %d exceeds 4096", n_splits * out_cap);
   int ns = 0;
   const bool bf = ix->fmt == ANCE_FMT_BF16;
-#define ANCE_COARSE(CG_, CAP_)                                                                                     \
-  rc = bf ? launch_coarse<256, (CG_ == 1 ? 4 : 6), CG_, CAP_, tc05::kFmtBF16>(ix, Q16, nq, kprime, n_splits, &ns, st) \
-          : launch_coarse<256, (CG_ == 1 ? 4 : 6), CG_, CAP_, tc05::kFmtF16>(ix, Q16, nq, kprime, n_splits, &ns, st)
+#define ANCE_COARSE(CG_, CAP_)                                                                                              \
+  rc = bf ? launch_coarse<256, (CG_ == 1 ? 4 : 6), CG_, CAP_, tc05::kFmtBF16>(ix, Q16, nq, kprime, out_cap, thr_init, n_splits, &ns, st) \
+          : launch_coarse<256, (CG_ == 1 ? 4 : 6), CG_, CAP_, tc05::kFmtF16>(ix, Q16, nq, kprime, out_cap, thr_init, n_splits, &ns, st)
   if (cg == 1 && cap == 1024) { ANCE_COARSE(1, 1024); }
   else if (cg == 1) { ANCE_COARSE(1, 2048); }
   else if (cap == 1024) { ANCE_COARSE(2, 1024); }
@@ -758,27 +862,33 @@ int coarse_rescore_pass(ance_index* ix, const uint16_t* Q16, const float* q_f32,
   rp.cand_cnt = ix->cand_cnt;
   rp.cand_thr = ix->cand_thr;
   rp.n_splits = ns;
-  rp.kprime = kprime;
+  rp.cand_stride = out_cap;
   rp.k = k;
   rp.qn_hat = ix->qn_hat;
   rp.qn_delta = ix->qn_delta;
   rp.pstats = ix->pstats;
-  rp.accum_rel = 3.0517578125e-5f;  // 2^-15, see DESIGN.md "certificate"
+  // Accumulation error of the coarse score c = fl(sum_i q^_i p^_i) on the tensor core.  The 16-bit x 16-bit products
+  // are exact in fp32; what is unspecified is how tcgen05.mma adds them (PTX: "precision at least that of fp32", order
+  // and rounding implementation-defined; published measurements of earlier generations: truncation, block adds of
+  // K = 16 aligned to the largest exponent).  Any such scheme performs at most d + d/16 additions, each with an error
+  // of at most one ulp of the largest partial sum, 2^-23 * sum_i |q^_i p^_i| <= 2^-23 ||q^|| ||p^|| (Cauchy-Schwarz):
+  //   |c - <q^, p^>| <= (17/16) d 2^-23 ||q^|| ||p^||  <  d * 2^-22 * ||q^|| ||p^||          (d = 768: 1.83e-4)
+  // tests/test_gpu_search.py measures the real error against an fp64 dot of the same rounded operands (it is ~300x
+  // smaller: rounding errors average out, the bound does not assume they do).
+  rp.accum_rel = static_cast<float>(ix->dim) * 2.384185791015625e-07f;
   rp.D = D_dev;
   rp.I = I_dev;
   rp.row_offset = row_offset;
   rp.qlist = qlist;
   rp.flagged_list = flagged_out;
+  rp.flagged_thr = flagged_thr_out;
   rp.flag_slot = flag_slot;
   rp.counters = ix->counters;
   rp.max_eps = reinterpret_cast<unsigned int*>(ix->counters + 2);
-  rp.sort_n = next_pow2(ns * kprime);
+  rp.sort_n = next_pow2(ns * out_cap);
   const size_t rs_smem = static_cast<size_t>(rp.sort_n) * 8 + static_cast<size_t>(ix->dim) * 4 + (ns + 1) * 4 + 16;
-  static size_t rs_attr = 0;
-  if (rs_smem > 48 * 1024 && rs_smem > rs_attr) {
+  if (rs_smem > 48 * 1024)   // per device and cheap: no process-wide cache
     ANCE_CUDA(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem)));
-    rs_attr = rs_smem;
-  }
   ance::prof_begin(ance::kClsRescore, st);
   rescore_kernel<<<static_cast<unsigned>(nq), 256, rs_smem, st>>>(rp);
   ance::prof_end(ance::kClsRescore, st);
@@ -787,9 +897,7 @@ int coarse_rescore_pass(ance_index* ix, const uint16_t* Q16, const float* q_f32,
   return ANCE_OK;
 }
 
-}  // namespace
-
-extern "C" int ance_index_create(int dim, int64_t capacity_rows, int operand_fmt, ance_index_t* out) {
+int create_common(int dim, int64_t capacity_rows, int operand_fmt, float* external_rows, ance_index_t* out) {
   ANCE_REQUIRE(out != nullptr, "ance_index_create: out is null");
   ANCE_REQUIRE(dim > 0 && dim % 8 == 0 && dim <= 4096, "ance_index_create: dim must be a multiple of 8 in (0, 4096], got %d", dim);
   ANCE_REQUIRE(capacity_rows > 0 && capacity_rows < (1ll << 31), "ance_index_create: capacity_rows out of range");
@@ -802,28 +910,61 @@ extern "C" int ance_index_create(int dim, int64_t capacity_rows, int operand_fmt
   ix->fmt = operand_fmt;
   cudaGetDevice(&ix->device);
   const size_t elems = static_cast<size_t>(capacity_rows) * dim;
-  cudaError_t e1 = cudaMalloc(&ix->P32, elems * 4);
+  cudaError_t e1 = cudaSuccess;
+  if (external_rows) {
+    ix->P32 = external_rows;
+    ix->owns_p32 = false;
+  } else {
+    e1 = cudaMalloc(&ix->P32, elems * 4);
+  }
   cudaError_t e2 = cudaMalloc(&ix->P16, elems * 2);
   cudaError_t e3 = cudaMalloc(&ix->pstats, 2 * sizeof(unsigned int));
-  cudaError_t e4 = cudaMalloc(&ix->err_flag, sizeof(int));
-  cudaError_t e5 = cudaMalloc(&ix->counters, 4 * sizeof(int));
+  cudaError_t e4 = cudaMalloc(&ix->pace, kMaxPace * sizeof(int));
+  cudaError_t e5 = cudaMalloc(&ix->counters, kNumCounters * sizeof(int));
   if (e1 || e2 || e3 || e4 || e5) {
     ance::set_error("ance_index_create: cudaMalloc failed for %lld x %d rows", (long long)capacity_rows, dim);
     ance_index_destroy(ix);
     return ANCE_ERR_NOMEM;
   }
   cudaMemset(ix->pstats, 0, 2 * sizeof(unsigned int));
-  cudaMemset(ix->err_flag, 0, sizeof(int));
-  cudaMemset(ix->counters, 0, 4 * sizeof(int));
+  cudaMemset(ix->counters, 0, kNumCounters * sizeof(int));
   *out = ix;
   return ANCE_OK;
 }
 
+int quantize_rows(ance_index* ix, int64_t first, int64_t n, cudaStream_t st) {
+  const float* src = ix->P32 + static_cast<size_t>(first) * ix->dim;
+  uint16_t* dst16 = ix->P16 + static_cast<size_t>(first) * ix->dim;
+  const int wpb = 8;
+  const unsigned blocks = static_cast<unsigned>((n + wpb - 1) / wpb);
+  ance::ProfScope ps(ance::kClsQuant, st);
+  if (ix->fmt == ANCE_FMT_BF16)
+    quantize_rows_kernel<true><<<blocks, wpb * 32, 0, st>>>(src, dst16, n, ix->dim, nullptr, nullptr, ix->pstats, ix->counters + kCntRowErr);
+  else
+    quantize_rows_kernel<false><<<blocks, wpb * 32, 0, st>>>(src, dst16, n, ix->dim, nullptr, nullptr, ix->pstats, ix->counters + kCntRowErr);
+  ANCE_CUDA(cudaGetLastError());
+  ance::count_launch(1);
+  return ANCE_OK;
+}
+
+}  // namespace
+
+extern "C" int ance_index_create(int dim, int64_t capacity_rows, int operand_fmt, ance_index_t* out) {
+  return create_common(dim, capacity_rows, operand_fmt, nullptr, out);
+}
+
+extern "C" int ance_index_create_over(int dim, int64_t capacity_rows, int operand_fmt, float* rows_dev,
+                                      ance_index_t* out) {
+  ANCE_REQUIRE(rows_dev != nullptr, "ance_index_create_over: rows_dev is null");
+  ANCE_REQUIRE((reinterpret_cast<uintptr_t>(rows_dev) & 15) == 0, "ance_index_create_over: rows_dev must be 16-byte aligned");
+  return create_common(dim, capacity_rows, operand_fmt, rows_dev, out);
+}
+
 extern "C" int ance_index_destroy(ance_index_t ix) {
   if (!ix) return ANCE_OK;
-  void* ptrs[] = {ix->P32, ix->P16, ix->pstats, ix->err_flag, ix->Q16, ix->qn_hat, ix->qn_delta, ix->scratch_sc,
-                  ix->scratch_id, ix->cand_id, ix->cand_cnt, ix->cand_thr, ix->flagged, ix->counters, ix->chunk_keys,
-                  ix->flagged2, ix->Q16b};
+  void* ptrs[] = {ix->owns_p32 ? ix->P32 : nullptr, ix->P16, ix->pstats, ix->Q16, ix->qn_hat, ix->qn_delta, ix->scratch_sc,
+                  ix->scratch_id, ix->cand_id, ix->cand_cnt, ix->cand_thr, ix->flagged, ix->flagged_thr, ix->counters,
+                  ix->chunk_keys, ix->flagged2, ix->Q16b, ix->pace};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ix;
@@ -834,6 +975,7 @@ extern "C" int ance_index_reset(ance_index_t ix) {
   ANCE_REQUIRE(ix != nullptr, "ance_index_reset: null handle");
   ix->n = 0;
   ANCE_CUDA(cudaMemset(ix->pstats, 0, 2 * sizeof(unsigned int)));
+  ANCE_CUDA(cudaMemset(ix->counters, 0, kNumCounters * sizeof(int)));
   return ANCE_OK;
 }
 
@@ -846,19 +988,13 @@ extern "C" int ance_index_add(ance_index_t ix, const float* rows_dev, int64_t n,
   ANCE_REQUIRE(rows_dev != nullptr, "ance_index_add: rows_dev is null");
   ANCE_REQUIRE(ix->n + n <= ix->cap, "ance_index_add: %lld + %lld rows exceed capacity %lld", (long long)ix->n,
                (long long)n, (long long)ix->cap);
+  int rc = check_handle_device(ix, "ance_index_add");
+  if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* dst = ix->P32 + static_cast<size_t>(ix->n) * ix->dim;
-  if (dst != rows_dev)
+  if (dst != rows_dev)   // rows produced in place (the encoder wrote straight into the index storage): no copy
     ANCE_CUDA(cudaMemcpyAsync(dst, rows_dev, static_cast<size_t>(n) * ix->dim * 4, cudaMemcpyDeviceToDevice, st));
-  uint16_t* dst16 = ix->P16 + static_cast<size_t>(ix->n) * ix->dim;
-  const int wpb = 8;
-  const unsigned blocks = static_cast<unsigned>((n + wpb - 1) / wpb);
-  if (ix->fmt == ANCE_FMT_BF16)
-    quantize_rows_kernel<true><<<blocks, wpb * 32, 0, st>>>(dst, dst16, n, ix->dim, nullptr, nullptr, ix->pstats, ix->err_flag);
-  else
-    quantize_rows_kernel<false><<<blocks, wpb * 32, 0, st>>>(dst, dst16, n, ix->dim, nullptr, nullptr, ix->pstats, ix->err_flag);
-  ANCE_CUDA(cudaGetLastError());
-  ance::count_launch(1);
+  if ((rc = quantize_rows(ix, ix->n, n, st))) return rc;
   ix->n += n;
   return ANCE_OK;
 }
@@ -872,6 +1008,20 @@ extern "C" int ance_index_set_param(ance_index_t ix, const char* name, double va
   else if (!strcmp(name, "exact_fallback")) { ix->exact_fallback = v != 0; }
   else if (!strcmp(name, "tier2")) { ix->tier2 = v != 0; }
   else if (!strcmp(name, "max_ctas")) { ANCE_REQUIRE(v >= 0, "max_ctas must be >= 0"); ix->max_ctas = v; }
+  else if (!strcmp(name, "pace_window")) { ANCE_REQUIRE(v >= 0 && v <= 4096, "pace_window must be in [0, 4096]"); ix->pace_window = v; }
+  else if (!strcmp(name, "operand_fmt")) {
+    // re-round the rows already in the index to the other 16-bit format (the fp32 rows are kept for exactly this)
+    ANCE_REQUIRE(v == ANCE_FMT_BF16 || v == ANCE_FMT_FP16, "operand_fmt must be ANCE_FMT_FP16 or ANCE_FMT_BF16");
+    int rc = check_handle_device(ix, "ance_index_set_param");
+    if (rc) return rc;
+    if (v != ix->fmt) {
+      ix->fmt = v;
+      ANCE_CUDA(cudaMemset(ix->pstats, 0, 2 * sizeof(unsigned int)));
+      ANCE_CUDA(cudaMemset(ix->counters + kCntRowErr, 0, sizeof(int)));
+      if (ix->n > 0 && (rc = quantize_rows(ix, 0, ix->n, nullptr))) return rc;
+      ANCE_CUDA(cudaDeviceSynchronize());
+    }
+  }
   else { ance::set_error("ance_index_set_param: unknown parameter '%s'", name); return ANCE_ERR_INVALID; }
   return ANCE_OK;
 }
@@ -882,6 +1032,8 @@ extern "C" int ance_index_search_exact(ance_index_t ix, const float* q_dev, int6
   ANCE_REQUIRE(nq >= 0 && k > 0 && k <= 512, "ance_index_search_exact: need nq >= 0 and 0 < k <= 512");
   if (nq == 0) return ANCE_OK;
   ANCE_REQUIRE(q_dev && D_dev && I_dev, "ance_index_search_exact: null buffer");
+  int rc = check_handle_device(ix, "ance_index_search_exact");
+  if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (ix->n == 0) {
     // faiss on an empty index: labels -1, scores lowest float
@@ -902,65 +1054,77 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
   ANCE_REQUIRE(k > 0, "ance_index_search: k must be positive");
   if (nq == 0) return ANCE_OK;
   ANCE_REQUIRE(q_dev && D_dev && I_dev, "ance_index_search: null buffer");
+  int rc = check_handle_device(ix, "ance_index_search");
+  if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // choose k' (candidates kept per split): >= k + 25% margin, multiple of 32
+  // choose k' (candidates kept per split).  The certificate needs every row within eps of the k-th score among the
+  // candidates; eps is ~0.5 (fp16 operands) / ~3 (bf16) for rows of norm 27.7, i.e. ~0.1 k / ~0.6 k extra rows on the
+  // distributions of tools/exp_certify.py.  A query that k' does not cover costs one tier-2 pass, not a wrong answer.
   int kprime = ix->kprime;
-  if (kprime == 0) kprime = (k <= 240) ? std::min(512, std::max(64, (2 * k + 32 + 31) / 32 * 32))
-                               : std::min(992, (2 * k + 31) / 32 * 32);
+  if (kprime == 0) {
+    const int want = (ix->fmt == ANCE_FMT_FP16) ? k + k / 2 - k / 16 : 2 * k + 32;   // fp16: ~1.44 k (k = 200: 288)
+    kprime = (k <= 240) ? std::min(512, std::max(64, (want + 31) / 32 * 32)) : std::min(992, (2 * k + 31) / 32 * 32);
+  }
   if (kprime < k || kprime > 992 || k > 512 || ix->n < 4 * static_cast<int64_t>(kprime)) {
     // tiny index or very large k: the exact brute-force path is both correct and cheap enough
     ANCE_REQUIRE(k <= 512, "ance_index_search: k = %d > 512 is not supported", k);
     ix->stats = ance_search_stats{};
     ix->stats.nq = nq;
     ix->stats.n_uncertified = nq;
-    ix->stats_pending = false;
     return ance_index_search_exact(ix, q_dev, nq, k, D_dev, I_dev, row_offset, stream);
   }
   // --- 1. quantize queries
-  int rc;
   {
     size_t a = static_cast<size_t>(ix->q_cap) * ix->dim, b = ix->q_cap, c = ix->q_cap;
     if ((rc = ensure(&ix->Q16, &a, static_cast<size_t>(nq) * ix->dim))) return rc;
     if ((rc = ensure(&ix->qn_hat, &b, static_cast<size_t>(nq)))) return rc;
     if ((rc = ensure(&ix->qn_delta, &c, static_cast<size_t>(nq)))) return rc;
     ix->q_cap = std::max<int64_t>(ix->q_cap, nq);
-    size_t f = ix->flagged_cap;
+    size_t f = ix->flagged_cap, g = ix->flagged_cap;
     if ((rc = ensure(&ix->flagged, &f, static_cast<size_t>(nq)))) return rc;
+    if ((rc = ensure(&ix->flagged_thr, &g, static_cast<size_t>(nq)))) return rc;
     ix->flagged_cap = f;
   }
-  ANCE_CUDA(cudaMemsetAsync(ix->counters, 0, 4 * sizeof(int), st));
+  ANCE_CUDA(cudaMemsetAsync(ix->counters, 0, kCntRowErr * sizeof(int), st));   // everything but the sticky row flag
   const unsigned qblocks = static_cast<unsigned>((nq + 7) / 8);
   ance::prof_begin(ance::kClsQuant, st);
   if (ix->fmt == ANCE_FMT_BF16)
-    quantize_rows_kernel<true><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, ix->qn_hat, ix->qn_delta, nullptr, ix->err_flag);
+    quantize_rows_kernel<true><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, ix->qn_hat, ix->qn_delta, nullptr, ix->counters + kCntQueryErr);
   else
-    quantize_rows_kernel<false><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, ix->qn_hat, ix->qn_delta, nullptr, ix->err_flag);
+    quantize_rows_kernel<false><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, ix->qn_hat, ix->qn_delta, nullptr, ix->counters + kCntQueryErr);
   ance::prof_end(ance::kClsQuant, st);
   ANCE_CUDA(cudaGetLastError());
   ance::count_launch(1);
   // --- 2+3. tier 1: coarse pass over all queries, exact rescoring, certificate
   int ns = 0;
-  rc = coarse_rescore_pass(ix, ix->Q16, q_dev, nq, nullptr, kprime, ix->n_splits, k, D_dev, I_dev, row_offset,
-                           ix->flagged, 0, &ns, st);
+  rc = coarse_rescore_pass(ix, ix->Q16, q_dev, nq, nullptr, kprime, nullptr, ix->n_splits, k, D_dev, I_dev, row_offset,
+                           ix->flagged, ix->flagged_thr, 0, &ns, st);
   if (rc) return rc;
-  // One small D2H + sync per search tells the host how many queries stay uncertified (the reference's
-  // search call is synchronous as well).
-  int h[4] = {0, 0, 0, 0};
+  // One small D2H + sync per search tells the host how many queries stay uncertified and whether an operand left
+  // the 16-bit format's range (the reference's search call is synchronous as well).
+  int h[kNumCounters] = {};
   ANCE_CUDA(cudaMemcpyAsync(h, ix->counters, sizeof(h), cudaMemcpyDeviceToHost, st));
   ANCE_CUDA(cudaStreamSynchronize(st));
+  if (h[kCntQueryErr] || h[kCntRowErr]) {
+    // coarse scores, thresholds and the certificate would be compared against inf / NaN: refuse instead of
+    // returning ANCE_OK with unverifiable neighbours
+    ance::set_error("ance_index_search: %s non-finite after rounding to %s (inf / NaN in the input%s)",
+                    h[kCntRowErr] ? "an index row is" : "a query is", ix->fmt == ANCE_FMT_FP16 ? "fp16" : "bf16",
+                    ix->fmt == ANCE_FMT_FP16 ? ", or |x| > 65504: switch with ance_index_set_param(\"operand_fmt\", ANCE_FMT_BF16)" : "");
+    return ANCE_ERR_UNSUPPORTED;
+  }
   int n_exact = h[0];
   int ns2 = 0;
-  const int kprime2 = 992;
-  if (h[0] > 0 && ix->tier2 && kprime < kprime2 && ix->n >= 4 * static_cast<int64_t>(kprime2)) {
-    // --- tier 2: the uncertified queries again with the widest reservoir (k' = 992)
+  if (h[0] > 0 && ix->tier2 && ix->n >= 4 * 992) {
+    // --- tier 2: the uncertified queries once more, from their own thresholds (nothing that passes is dropped)
     const int n2 = h[0];
     if ((rc = ensure(&ix->Q16b, &ix->q16b_elems, static_cast<size_t>(n2) * ix->dim))) return rc;
     if ((rc = ensure(&ix->flagged2, &ix->flagged2_cap, static_cast<size_t>(n2)))) return rc;
     gather_rows16_kernel<<<n2, 96, 0, st>>>(ix->Q16, ix->flagged, n2, ix->dim, ix->Q16b);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(1);
-    rc = coarse_rescore_pass(ix, ix->Q16b, q_dev, n2, ix->flagged, kprime2, 0, k, D_dev, I_dev, row_offset,
-                             ix->flagged2, 3, &ns2, st);
+    rc = coarse_rescore_pass(ix, ix->Q16b, q_dev, n2, ix->flagged, 992, ix->flagged_thr, 0, k, D_dev, I_dev, row_offset,
+                             ix->flagged2, nullptr, 3, &ns2, st);
     if (rc) return rc;
     ANCE_CUDA(cudaMemcpyAsync(h, ix->counters, sizeof(h), cudaMemcpyDeviceToHost, st));
     ANCE_CUDA(cudaStreamSynchronize(st));
@@ -983,22 +1147,11 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
   ix->stats.n_candidates = h[1];
   memcpy(&ix->stats.max_eps, &h[2], 4);
   ix->last_stream = st;
-  ix->stats_pending = true;
   return ANCE_OK;
 }
 
 extern "C" int ance_index_last_stats(ance_index_t ix, ance_search_stats* out) {
   ANCE_REQUIRE(ix != nullptr && out != nullptr, "ance_index_last_stats: null argument");
-  if (ix->stats_pending) {
-    int err = 0;
-    ANCE_CUDA(cudaStreamSynchronize(ix->last_stream));
-    ANCE_CUDA(cudaMemcpy(&err, ix->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-    ix->stats_pending = false;
-    if (err) {
-      ance::set_error("non-finite value after rounding to the 16-bit operand format (use ANCE_FMT_BF16 for data outside the fp16 range)");
-      return ANCE_ERR_UNSUPPORTED;
-    }
-  }
   *out = ix->stats;
   return ANCE_OK;
 }

@@ -149,48 +149,74 @@ class B200Backend:
         self.device = args.device
         self.mask_mode = mask_mode  # "lens": 1^len 0^(L-len) (msmarco_data.py:282); "nonzero": ids != 0 (DPR_data.py:283)
 
-    def encode(self, cache_path: str, is_query: bool) -> Tuple[torch.Tensor, np.ndarray]:
-        """This rank's records of one token cache -> (rows [n_rows, 768] fp32 CUDA, embedding2id int64)."""
+    def encode(self, cache_path: str, is_query: bool, build_index: bool = False):
+        """This rank's records of one token cache -> (rows [n_rows, 768] fp32 CUDA, embedding2id int64), or
+        (IndexFlatIP, rows, embedding2id) with build_index.
+
+        The rows of a rank are ONE pre-sized device tensor: every super-batch is encoded straight into its slice, and with
+        build_index that tensor IS the index's fp32 storage (ance_index_create_over), each slice being added in place as
+        soon as it is written.  The corpus therefore exists once in fp32 (+ once in 16 bits for the coarse pass) instead
+        of the reference's per-batch arrays + concatenation + faiss copy (run_ann_data_gen.py:160-193,271)."""
         args = self.args
         W, rank = _world()
         cache = EmbeddingCache(cache_path)
         L = cache.embedding_size
         multi = (not is_query) and hasattr(self.model, "encode_lens_multi_chunk") and L > 512
+        C = (L // 512) if multi else 1
         B = args.per_gpu_eval_batch_size
         per = max(B, (args.encode_batch_tokens // L) // B * B)  # super-batch, a multiple of the reference batch
         bucketed = self.mask_mode != "nonzero" and not multi and getattr(args, "length_buckets", True)
         if bucketed:
             per *= 8   # every length bucket of a super-batch should still fill the GPU (the encoder re-splits by tokens)
         reader = StridedBatchReader(cache, per, rank=rank, world_size=W)
-        outs: List[torch.Tensor] = []
+        n_rows = reader.n_local * C
+        dim = 768
+        rows = torch.empty((max(n_rows, 1), dim), dtype=torch.float32, device=self.device)[:n_rows]
+        index = None
+        if build_index:
+            from ..search import IndexFlatIP
+            index = IndexFlatIP(dim, device=self.device, operand=args.search_operand,
+                                storage=rows if n_rows else None, capacity=0 if n_rows else 1)
         ids_out: List[np.ndarray] = []
+        pos = 0
         with torch.no_grad():
             for ids, lens, idx in reader:
                 ids_d = ids.to(self.device, non_blocking=True)
                 lens_d = lens.to(self.device, non_blocking=True)
+                out = rows[pos:pos + ids.shape[0] * C]
                 if self.mask_mode == "nonzero":
                     fn = self.model.query_emb if is_query else self.model.body_emb
-                    e, i = fn(ids_d, ids_d != 0), idx.numpy()
+                    out.copy_(fn(ids_d, ids_d != 0))
+                    i = idx.numpy()
                 elif multi:
                     e = self.model.encode_lens_multi_chunk(ids_d, lens_d)
                     e, i = rows_from_batches(e, idx.numpy(), B)
-                elif getattr(args, "length_buckets", True):
-                    e, i = self.model.encode_lens_bucketed(ids_d, lens_d), idx.numpy()
+                    out.copy_(e)
+                elif bucketed:
+                    self.model.encode_lens_bucketed(ids_d, lens_d, out=out)
+                    i = idx.numpy()
                 else:
-                    e, i = self.model.encode_lens(ids_d, lens_d), idx.numpy()
-                outs.append(e)
+                    self.model.encode_lens(ids_d, lens_d, out=out)
+                    i = idx.numpy()
+                if index is not None:
+                    index.add(out)     # in place: quantise to the 16-bit operands, no copy
                 ids_out.append(i)
+                pos += out.shape[0]
         if hasattr(self.model, "check_inputs"):
             self.model.check_inputs()   # out-of-vocabulary ids: fail like the reference's embedding lookup does
-        if outs:
-            return torch.cat(outs, dim=0), np.concatenate(ids_out)
-        return torch.empty((0, 768), dtype=torch.float32, device=self.device), np.empty((0,), dtype=np.int64)
+        emb2id = np.concatenate(ids_out) if ids_out else np.empty((0,), dtype=np.int64)
+        return (index, rows, emb2id) if build_index else (rows, emb2id)
 
-    def make_local_search(self, passages: torch.Tensor) -> Callable:
+    def make_local_search(self, passages) -> Callable:
+        """passages: an IndexFlatIP built by encode(build_index=True), or a [n, 768] CUDA tensor (copied into a new one)."""
         from ..search import IndexFlatIP
-        index = IndexFlatIP(passages.shape[1], capacity=max(1, passages.shape[0]), device=self.device,
-                            operand=self.args.search_operand)
-        index.add(passages)
+        if isinstance(passages, IndexFlatIP):
+            index = passages
+        else:
+            index = IndexFlatIP(passages.shape[1], capacity=max(1, passages.shape[0]), device=self.device,
+                                operand=self.args.search_operand)
+            index.add(passages)
+        self.index = index
         return lambda q, k, row_offset: index.search_device(q, k, row_offset=row_offset)
 
 
@@ -226,26 +252,123 @@ def all_gather_ids(ids: np.ndarray, device) -> np.ndarray:
     return all_gather_rows(t[:, None])[:, 0].cpu().numpy()
 
 
+#: queries per search block: 74 CTA pairs x 256 query rows = one full wave of the coarse kernel on a B200
+QUERY_BLOCK = 18944
+
+
+class _Staging:
+    """Pinned host staging for one in-flight block (reused: a block's buffers are free again once its merge is done)."""
+
+    def __init__(self, rows: int, k: int, with_scores: bool, pin: bool):
+        self.D = torch.empty((rows, k), dtype=torch.float32, pin_memory=pin) if with_scores else None
+        self.I = torch.empty((rows, k), dtype=torch.int64, pin_memory=pin)
+        self.job = None
+
+
 def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch.Tensor, k: int,
-                   merge_threads: int = 0) -> Optional[np.ndarray]:
-    """Every rank searches its own rows for ALL queries; rank 0 merges.  Returns I [nq, k] (global rows)
-    on rank 0, None elsewhere."""
+                   merge_threads: int = 0, query_block: int = QUERY_BLOCK, gather_to_rank0: bool = True
+                   ) -> Optional[np.ndarray]:
+    """Every rank searches its own rows for ALL queries; the per-shard top-k lists of a query are merged on the rank
+    that OWNS the query, so the merge (and its device->host copy) is spread over all ranks instead of serialised on
+    rank 0, and it overlaps the search of the next query block:
+
+        for each block of `query_block` queries                        (device work on the current stream)
+            D, I = local_search(block)                                   per-shard top-k, labels already global
+            all_to_all(D), all_to_all(I)                                 rank r receives the W lists of ITS 1/W of the block
+            async D2H into pinned staging  ->  host k-way merge (C++, worker thread)      || next block's search
+
+    Returns I [nq, k] (global rows, merged order) on rank 0 and None elsewhere; with gather_to_rank0=False every rank
+    gets the merged lists of the queries it owns as (I_own [n_own, k], own_query_numbers)."""
+    from concurrent.futures import ThreadPoolExecutor
     from ..search import merge_topk_host
     W, rank = _world()
-    sizes = _shard_sizes(n_local_rows, queries_all.device)
+    dev = queries_all.device
+    cuda = dev.type == "cuda"
+    sizes = _shard_sizes(n_local_rows, dev)
     offset = int(sum(sizes[:rank]))
-    D, I = local_search(queries_all, k, offset)
+    nq = int(queries_all.shape[0])
+    QB = max(W, (max(1, min(query_block, nq)) + W - 1) // W * W)      # a multiple of W: equal all-to-all splits
+    part = QB // W
+    side = torch.cuda.Stream(device=dev) if cuda else None
+    stage = [_Staging(QB, k, W > 1, cuda) for _ in range(2)]
+    pool = ThreadPoolExecutor(max_workers=1)
+    own_I: List[np.ndarray] = []
+    own_q: List[np.ndarray] = []
+
+    def finish(st: _Staging, ev, n_valid: int, q0: int):
+        if ev is not None:
+            ev.synchronize()
+        if W == 1:
+            own_I.append(st.I[:n_valid].numpy().copy())
+        else:
+            Dv, Iv = st.D.numpy().reshape(W, part, k), st.I.numpy().reshape(W, part, k)
+            _, Im = merge_topk_host([Dv[s, :n_valid] for s in range(W)], [Iv[s, :n_valid] for s in range(W)], k,
+                                    merge_threads)
+            own_I.append(Im)
+        own_q.append(np.arange(q0, q0 + n_valid, dtype=np.int64))
+
+    for bi, b0 in enumerate(range(0, nq, QB)):
+        nb = min(QB, nq - b0)
+        qb = queries_all[b0:b0 + nb]
+        if nb < QB and W > 1:      # ragged last block: pad so that every rank owns the same number of rows
+            qb = torch.cat([qb, qb.new_zeros((QB - nb, qb.shape[1]))], dim=0)
+        D, I = local_search(qb.contiguous(), k, offset)
+        st = stage[bi % 2]
+        if st.job is not None:
+            st.job.result()        # the staging buffers are free again
+        if W > 1:
+            Dr, Ir = torch.empty_like(D), torch.empty_like(I)
+            dist.all_to_all_single(Dr, D)          # Dr[s*part:(s+1)*part] = shard s's lists for my part of the block
+            dist.all_to_all_single(Ir, I)
+            n_valid = max(0, min(part, nb - rank * part))
+            q0 = b0 + rank * part
+        else:
+            Dr, Ir, n_valid, q0 = None, I, nb, b0
+        ev = None
+        if cuda:
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                if Dr is not None:
+                    st.D.copy_(Dr, non_blocking=True)
+                    Dr.record_stream(side)
+                st.I[:Ir.shape[0]].copy_(Ir, non_blocking=True)
+                Ir.record_stream(side)
+                ev = torch.cuda.Event()
+                ev.record(side)
+        else:
+            if Dr is not None:
+                st.D.copy_(Dr)
+            st.I[:Ir.shape[0]].copy_(Ir)
+        st.job = pool.submit(finish, st, ev, n_valid, q0)
+    for st in stage:
+        if st.job is not None:
+            st.job.result()
+    pool.shutdown()
+    I_own = np.concatenate(own_I) if own_I else np.empty((0, k), dtype=np.int64)
+    q_own = np.concatenate(own_q) if own_q else np.empty((0,), dtype=np.int64)
+    if not gather_to_rank0:
+        return I_own, q_own
     if W == 1:
-        return I.cpu().numpy()
+        return I_own
+    # final assembly on rank 0 (post-processing and the output files are rank 0's, run_ann_data_gen.py:265-336):
+    # nq x k labels in total, 1/W of what a gather of the per-shard lists would move
+    n_blocks = (nq + QB - 1) // QB
+    mine = torch.full((n_blocks * part, k), -1, dtype=torch.int64)
+    mine[:I_own.shape[0]] = torch.from_numpy(I_own)
+    mine = mine.to(dev)
     if rank == 0:
-        Ds = [torch.empty_like(D) for _ in range(W)]
-        Is = [torch.empty_like(I) for _ in range(W)]
-        dist.gather(D, Ds, dst=0)
-        dist.gather(I, Is, dst=0)
-        _, Im = merge_topk_host([d.cpu().numpy() for d in Ds], [i.cpu().numpy() for i in Is], k, merge_threads)
-        return Im
-    dist.gather(D, None, dst=0)
-    dist.gather(I, None, dst=0)
+        parts = [torch.empty_like(mine) for _ in range(W)]
+        dist.gather(mine, parts, dst=0)
+        out = np.empty((nq, k), dtype=np.int64)
+        for r in range(W):
+            pr = parts[r].cpu().numpy()
+            row = 0
+            for b0 in range(0, nq, QB):
+                nv = max(0, min(part, min(QB, nq - b0) - r * part))
+                out[b0 + r * part:b0 + r * part + nv] = pr[row:row + nv]
+                row += nv
+        return out
+    dist.gather(mine, None, dst=0)
     return None
 
 
@@ -274,7 +397,7 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
     logger.info("***** inference of dev query *****")
     dev_emb, dev_ids = backend.encode(os.path.join(args.data_dir, "dev-query"), True)
     logger.info("***** inference of passages *****")
-    p_emb, p_ids = backend.encode(os.path.join(args.data_dir, "passages"), False)
+    index, p_emb, p_ids = backend.encode(os.path.join(args.data_dir, "passages"), False, build_index=True)
     logger.info("***** Done passage inference *****")
     if args.inference:
         _dump(args, "dev_query_" + step + "_", dev_emb, dev_ids)
@@ -285,7 +408,7 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
     t_enc = time.time()
 
     device = p_emb.device
-    local_search = backend.make_local_search(p_emb)
+    local_search = backend.make_local_search(index)
     passage_embedding2id = all_gather_ids(p_ids, device)
     dev_all, dev_query_embedding2id = all_gather_rows(dev_emb), all_gather_ids(dev_ids, device)
     q_all, query_embedding2id = all_gather_rows(q_emb), all_gather_ids(q_ids, device)
@@ -314,6 +437,8 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
                                     query_embedding2id, training_query_positive_id, negatives, sampler=sampler,
                                     seed=args.seed)
     postprocess.write_ndcg(os.path.join(args.output_dir, "ann_ndcg_" + str(output_num)), dev_ndcg, checkpoint_path)
+    args.last_refresh_timing = {"encode_s": t_enc - t_start, "search_s": t_search - t_enc, "post_s": time.time() - t_search,
+                                "search_stats": backend.index.stats() if hasattr(backend, "index") else None}
     logger.info("refresh %d: encode %.1fs search %.1fs post %.1fs", output_num, t_enc - t_start, t_search - t_enc,
                 time.time() - t_search)
     return dev_ndcg, num_queries_dev
@@ -350,8 +475,9 @@ def get_arguments(argv=None):
     p.add_argument("--config_name", default="", type=str)
     p.add_argument("--tokenizer_name", default="", type=str)
     # B200 knobs (not in the reference)
-    p.add_argument("--search_operand", default="bf16", choices=["bf16", "fp16"],
-                   help="16-bit operand format of the coarse tensor-core pass (results are exact either way)")
+    p.add_argument("--search_operand", default="auto", choices=["auto", "fp16", "bf16"],
+                   help="16-bit operand format of the coarse tensor-core pass (results are exact either way); auto = fp16, "
+                        "falling back to bf16 when a row or a query leaves the fp16 range")
     p.add_argument("--encode_batch_tokens", default=75776, type=int, help="tokens per encoder launch sequence")
     p.add_argument("--reference_sampling", default=False, action="store_true",
                    help="draw the negative-sampling order from Python's `random` exactly as the reference does")

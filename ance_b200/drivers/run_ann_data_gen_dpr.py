@@ -137,9 +137,9 @@ def generate_new_ann(args, output_num, checkpoint_path, preloaded_data, latest_s
     q_emb, q_ids = backend.encode(os.path.join(d, "train-query"), True)
     dev_emb, dev_ids = backend.encode(os.path.join(d, "test-query"), True)
     tv_emb, tv_ids = backend.encode(os.path.join(d, "trivia-test-query"), True)
-    p_emb, p_ids = backend.encode(os.path.join(d, "passages"), False)
+    index, p_emb, p_ids = backend.encode(os.path.join(d, "passages"), False, build_index=True)
     device = p_emb.device
-    local_search = backend.make_local_search(p_emb)
+    local_search = backend.make_local_search(index)
     passage_embedding2id = all_gather_ids(p_ids, device)
     sets = {}
     for name, (e, i) in {"train": (q_emb, q_ids), "dev": (dev_emb, dev_ids), "trivia": (tv_emb, tv_ids)}.items():
@@ -197,7 +197,7 @@ def get_arguments(argv=None):
     p.add_argument("--test_qa_path", default=None, type=str, required=True)
     p.add_argument("--trivia_test_qa_path", default=None, type=str, required=True)
     # B200 knobs
-    p.add_argument("--search_operand", default="bf16", choices=["bf16", "fp16"])
+    p.add_argument("--search_operand", default="auto", choices=["auto", "fp16", "bf16"])
     p.add_argument("--encode_batch_tokens", default=75776, type=int)
     p.add_argument("--seed", default=None, type=int)
     p.add_argument("--poll_seconds", default=60, type=int)

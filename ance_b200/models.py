@@ -80,7 +80,7 @@ class _CudaEncoder:
     """Owns one ance_encoder handle built from a backbone's current parameters."""
 
     def __init__(self, backbone: nn.Module, arch: int, heads: int, pad_id: int, head: Optional[tuple],
-                 max_tokens: int, device: torch.device):
+                 max_tokens: int, device: torch.device, operand: str = "fp16"):
         lib = _lib.load()
         self.lib = lib
         self.device = device
@@ -99,6 +99,8 @@ class _CudaEncoder:
         cfg.pad_id = pad_id
         cfg.ln_eps = float(emb.LayerNorm.eps)
         cfg.has_head = 1 if head is not None else 0
+        cfg.operand_fmt = {"fp16": _lib.ANCE_FMT_FP16, "bf16": _lib.ANCE_FMT_BF16}[operand]
+        self.operand = operand
         keep = []  # host arrays must outlive the create call
 
         def fp(t):
@@ -160,10 +162,15 @@ class _CudaEncoder:
             _lib.check(self.lib.ance_encoder_debug_hidden(self.h, layer, buf.data_ptr(), _lib.current_stream()))
         return buf[:n_tokens]
 
-    def forward(self, ids: torch.Tensor, lens: Optional[torch.Tensor], mask: Optional[torch.Tensor]) -> torch.Tensor:
-        """ids int32 [B, L] CUDA; exactly one of lens int32 [B] / mask uint8 [B, L].  -> fp32 [B, H]."""
+    def forward(self, ids: torch.Tensor, lens: Optional[torch.Tensor], mask: Optional[torch.Tensor],
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ids int32 [B, L] CUDA; exactly one of lens int32 [B] / mask uint8 [B, L].  -> fp32 [B, H] (written into `out`
+        when given: a contiguous fp32 CUDA tensor [B, H], e.g. a slice of an index's row storage)."""
         B, L = ids.shape
-        out = torch.empty((B, self.hidden_size), dtype=torch.float32, device=ids.device)
+        if out is None:
+            out = torch.empty((B, self.hidden_size), dtype=torch.float32, device=ids.device)
+        elif out.shape != (B, self.hidden_size) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != ids.device:
+            raise ValueError("out must be a contiguous float32 tensor [B, hidden] on the inputs' device")
         per = max(1, min(self.max_tokens // L, self.max_tokens // 16))
         with torch.cuda.device(ids.device):
             st = _lib.current_stream()
@@ -182,23 +189,37 @@ class _B200Encoder(nn.Module):
     #: every encoder GEMM then has a tile count divisible by the 74 CTA pairs of a B200 (no partial last wave).
     max_tokens = int(os.environ.get("ANCE_B200_MAX_TOKENS", 75776))
 
+    #: 16-bit storage format of weights and activations inside the CUDA encoder: "fp16" (11 significant bits; the
+    #: embeddings land within ~1e-2 of the reference's fp32 forward) or "bf16" (8 bits, for a checkpoint whose
+    #: activations leave the fp16 range — `check_inputs()` raises on the non-finite embeddings that produces).
+    #: Same tensor-core rate either way.
+    encoder_operand = os.environ.get("ANCE_B200_ENCODER_OPERAND", "fp16")
+
     def _enc_for(self, name, backbone, arch, heads, pad_id, head, device) -> _CudaEncoder:
         if device.type != "cuda":
             raise _lib.AnceError("ance_b200 models run on an sm_100 GPU only (no CPU fallback): move the model and "
                                  "the inputs to a CUDA device")
         cache = self.__dict__.setdefault("_enc_cache", {})
-        ver = tuple(p._version for p in self.parameters()) + (str(device),)
+        # Rebuild the device copy when a parameter was written in place (load_state_dict / optimizer step bump
+        # `_version`) or the module moved (`.to()` swaps `.data`: new storage).  The Parameter objects themselves are
+        # stable, so the module tree is walked once and ~200 version counters are summed per call, not re-collected.
+        params = cache.get("_params")
+        if params is None:
+            params = cache["_params"] = list(self.parameters())
+        ver = (sum(p._version for p in params), params[0].data_ptr(), str(device), self.encoder_operand)
         hit = cache.get(name)
         if hit is None or hit[0] != ver:
-            cache[name] = (ver, _CudaEncoder(backbone, arch, heads, pad_id, head, self.max_tokens, device))
+            cache[name] = (ver, _CudaEncoder(backbone, arch, heads, pad_id, head, self.max_tokens, device,
+                                             self.encoder_operand))
         return cache[name][1]
 
     def check_inputs(self) -> None:
         """Deferred input validation (keeps `body_emb`/`query_emb` asynchronous): raises if any encode since the last
         call saw a token id outside the vocabulary or a position beyond max_position_embeddings, where the reference's
         nn.Embedding lookup raises an IndexError.  Synchronises the current stream; the drivers call it per pass."""
-        for _, enc in self.__dict__.get("_enc_cache", {}).values():
-            enc.check()
+        for key, val in self.__dict__.get("_enc_cache", {}).items():
+            if key != "_params":
+                val[1].check()
 
     @staticmethod
     def _prep(input_ids, attention_mask):
@@ -299,10 +320,11 @@ class RobertaDot_NLL_LN(_B200Encoder):
         return self.query_emb(input_ids, attention_mask)
 
     # fast path used by the B200 refresher: mask given as lengths (msmarco_data.py:282 form)
-    def encode_lens(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor) -> torch.Tensor:
-        return self._encoder(ids_i32.device).forward(ids_i32.contiguous(), lens_i32.contiguous(), None)
+    def encode_lens(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._encoder(ids_i32.device).forward(ids_i32.contiguous(), lens_i32.contiguous(), None, out=out)
 
-    def encode_lens_bucketed(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor, min_bucket: int = 16) -> torch.Tensor:
+    def encode_lens_bucketed(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor, min_bucket: int = 16,
+                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Same result as encode_lens, without the FLOPs of all-padding tails: sequences are grouped by the
         smallest supported padded length >= their own length (16/32/64/128/256/384/512) and each group is
         encoded at that length.  Padding keys carry the additive -10000 (probability exactly 0 in fp32) and
@@ -313,7 +335,8 @@ class RobertaDot_NLL_LN(_B200Encoder):
             buckets.append(L)
         bt = torch.tensor(buckets, device=lens_i32.device, dtype=torch.int32)
         which = torch.bucketize(lens_i32.clamp(min=1), bt)  # first bucket with capacity >= len
-        out = torch.empty((B, 768), dtype=torch.float32, device=ids_i32.device)
+        if out is None:
+            out = torch.empty((B, 768), dtype=torch.float32, device=ids_i32.device)
         for bi, Lb in enumerate(buckets):
             sel = torch.nonzero(which == bi).flatten()
             if sel.numel() == 0:

@@ -43,16 +43,30 @@ class IndexFlatIP:
     """Exact maximum-inner-product search over fp32 rows resident in HBM."""
 
     def __init__(self, d: int, capacity: int = 0, device: Optional[torch.device] = None,
-                 operand: str = "bf16"):
+                 operand: str = "auto", storage: Optional[torch.Tensor] = None):
+        """operand: 16-bit format of the coarse tensor-core pass — "fp16" (certificate error bound ~8x tighter than bf16:
+        fewer candidates to rescore), "bf16" (any fp32 range), or "auto" = fp16, switching the whole index to bf16 the
+        first time a row or a query does not fit the fp16 range.  Results are exact either way.
+        storage: a CUDA fp32 tensor [capacity, d] to use as the index's row storage (kept alive by the index).  Rows
+        written into `storage[i:i+n]` by their producer and then passed to add() are added without a copy."""
         if not torch.cuda.is_available():
             raise _lib.AnceError("ance_b200.IndexFlatIP needs a CUDA device (sm_100); there is no CPU fallback")
         self._lib = _lib.load()
         self.d = int(d)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.operand = {"bf16": _lib.ANCE_FMT_BF16, "fp16": _lib.ANCE_FMT_FP16}[operand]
+        self.auto_operand = operand == "auto"
+        self.operand = {"bf16": _lib.ANCE_FMT_BF16, "fp16": _lib.ANCE_FMT_FP16, "auto": _lib.ANCE_FMT_FP16}[operand]
         self._h = None
         self._capacity = 0
         self.ntotal = 0
+        self.storage = None
+        if storage is not None:
+            if (storage.device.type != "cuda" or storage.dtype != torch.float32 or storage.dim() != 2
+                    or storage.shape[1] != self.d or not storage.is_contiguous()):
+                raise ValueError("storage must be a contiguous CUDA float32 tensor [capacity, d]")
+            self.device = storage.device
+            self.storage = storage
+            capacity = storage.shape[0]
         if capacity:
             self._create(int(capacity))
 
@@ -60,7 +74,11 @@ class IndexFlatIP:
     def _create(self, capacity: int):
         h = C.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.ance_index_create(self.d, capacity, self.operand, C.byref(h)))
+            if self.storage is not None:
+                _lib.check(self._lib.ance_index_create_over(self.d, capacity, self.operand, self.storage.data_ptr(),
+                                                            C.byref(h)))
+            else:
+                _lib.check(self._lib.ance_index_create(self.d, capacity, self.operand, C.byref(h)))
         self._h = h
         self._capacity = capacity
 
@@ -101,7 +119,8 @@ class IndexFlatIP:
                 xs = _as_f32_cuda(x[s:s + step], self.device)
                 _lib.check(self._lib.ance_index_add(self._h, xs.data_ptr(), xs.shape[0], _lib.current_stream()))
                 self.ntotal += xs.shape[0]
-            torch.cuda.current_stream().synchronize()
+            if step != n:   # host input: the pinned staging tensors must outlive their copies
+                torch.cuda.current_stream().synchronize()
 
     # -- search ------------------------------------------------------------------------------------
     def search_device(self, q: torch.Tensor, k: int, row_offset: int = 0, exact: bool = False
@@ -118,8 +137,16 @@ class IndexFlatIP:
             return D, I
         fn = self._lib.ance_index_search_exact if exact else self._lib.ance_index_search
         with torch.cuda.device(self.device):
-            _lib.check(fn(self._h, q.data_ptr(), nq, int(k), D.data_ptr(), I.data_ptr(), int(row_offset),
-                          _lib.current_stream()))
+            rc = fn(self._h, q.data_ptr(), nq, int(k), D.data_ptr(), I.data_ptr(), int(row_offset),
+                    _lib.current_stream())
+            if rc == _lib.ANCE_ERR_UNSUPPORTED and self.auto_operand and self.operand == _lib.ANCE_FMT_FP16:
+                # a row or a query left the fp16 range: re-round the index to bf16 (from its fp32 rows) and retry once;
+                # inf / NaN in the data fails again and raises
+                self.set_param("operand_fmt", _lib.ANCE_FMT_BF16)
+                self.operand = _lib.ANCE_FMT_BF16
+                rc = fn(self._h, q.data_ptr(), nq, int(k), D.data_ptr(), I.data_ptr(), int(row_offset),
+                        _lib.current_stream())
+            _lib.check(rc)
         return D, I
 
     def search(self, x, k: int):

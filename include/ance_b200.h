@@ -44,12 +44,14 @@ int64_t ance_launch_count(void);
  * when fewer than k rows exist the tail is label -1 / score -FLT_MAX.  Ties are broken by the
  * smaller row number (faiss leaves tie order unspecified; ours is deterministic).
  * Scores are the exact fp32-input dot product accumulated in fp64 and rounded once to fp32.
+ * ance_index_search fails with ANCE_ERR_UNSUPPORTED when an index row or a query is non-finite after rounding to the
+ * 16-bit operand format (inf / NaN input, or |x| > 65504 with ANCE_FMT_FP16) instead of returning unverifiable results.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct ance_index* ance_index_t;
 
 typedef struct {
   int64_t nq;             /* queries in the last search */
-  int64_t n_tier2;        /* queries the first coarse pass could not certify -> second pass with k' = 992 */
+  int64_t n_tier2;        /* queries the first coarse pass could not certify -> second pass from their own thresholds */
   int64_t n_uncertified;  /* queries no coarse pass could certify -> exact brute-force fallback */
   int64_t n_candidates;   /* candidates rescored in fp32/fp64 */
   int32_t kprime;         /* candidates kept per (query, split) by the coarse pass */
@@ -58,6 +60,12 @@ typedef struct {
 } ance_search_stats;
 
 int ance_index_create(int dim, int64_t capacity_rows, int operand_fmt, ance_index_t* out);
+/* Same, over CALLER-OWNED fp32 row storage rows_dev [capacity_rows, dim] (16-byte aligned, must outlive the index; never
+ * freed by it).  A producer that writes rows i .. i+n straight into rows_dev + i*dim and then calls
+ * ance_index_add(idx, rows_dev + i*dim, n) adds them WITHOUT a copy: this is how the refresher keeps one fp32 copy of the
+ * corpus instead of the reference's three (per-batch arrays -> concatenation -> faiss storage,
+ * drivers/run_ann_data_gen.py:160-193,271). */
+int ance_index_create_over(int dim, int64_t capacity_rows, int operand_fmt, float* rows_dev, ance_index_t* out);
 int ance_index_destroy(ance_index_t idx);
 int ance_index_reset(ance_index_t idx);                       /* ntotal = 0, storage kept */
 int64_t ance_index_ntotal(ance_index_t idx);
@@ -69,11 +77,12 @@ int ance_index_search(ance_index_t idx, const float* q_dev, int64_t nq, int k, f
 /* Same contract, computed entirely by the exact fp32->fp64 brute-force kernel (validation path). */
 int ance_index_search_exact(ance_index_t idx, const float* q_dev, int64_t nq, int k, float* D_dev,
                             int64_t* I_dev, int64_t row_offset, void* stream);
-/* Blocks on the stream of the last search and returns its statistics. */
+/* Statistics of the last search (ance_index_search has already synchronised its stream). */
 int ance_index_last_stats(ance_index_t idx, ance_search_stats* out);
-/* Tunables: "kprime" (0 = auto: about 2k), "n_splits" (0 = auto), "cta_group" (1|2), "max_ctas" (0 = all
- * SMs), "tier2" (0|1), "exact_fallback" (0|1: measurement only — results of uncertified queries are then
- * NOT guaranteed). */
+/* Tunables: "kprime" (0 = auto: about 1.44 k for fp16 operands, 2 k for bf16), "n_splits" (0 = auto), "cta_group" (1|2),
+ * "max_ctas" (0 = all SMs), "tier2" (0|1), "exact_fallback" (0|1: measurement only — results of uncertified queries are
+ * then NOT guaranteed), "pace_window" (tiles a sweeping CTA pair may run ahead of the slowest one; 0 = no soft
+ * barrier), "operand_fmt" (ANCE_FMT_*: re-rounds the rows already added from the fp32 copy). */
 int ance_index_set_param(ance_index_t idx, const char* name, double value);
 
 /* Host k-way merge of per-shard results — replaces utils/util.py:87-146 barrier_array_merge +
@@ -98,10 +107,16 @@ typedef struct {
   int n_layer, hidden, heads, ffn, vocab, max_pos, type_vocab, pad_id;
   float ln_eps;
   int has_head;    /* 1: out = LayerNorm(Linear(CLS)) (models.py:152-153); 0: out = CLS (models.py:237-239) */
+  int operand_fmt; /* ANCE_FMT_FP16 (recommended) or ANCE_FMT_BF16: 16-bit storage format of weights and activations.
+                      Both run the tensor cores at the same rate with fp32 accumulation; fp16 keeps 11 significant bits
+                      instead of 8, i.e. 8x closer to the reference's fp32 forward.  A checkpoint whose activations
+                      leave the fp16 range (|x| > 65504) produces non-finite embeddings, which ance_encoder_check
+                      reports as ANCE_ERR_UNSUPPORTED: use ANCE_FMT_BF16 for such a model. */
 } ance_encoder_config;
 
 /* All weight pointers are HOST fp32 arrays in the checkpoint's own layout (Linear weight = [out, in]);
- * the library converts and uploads them once. */
+ * the library converts and uploads them once (Linear weights -> operand_fmt; embedding tables, biases and LayerNorm
+ * parameters stay fp32). */
 typedef struct {
   const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b;   /* attention.self.{query,key,value} */
   const float *ao_w, *ao_b, *ln1_g, *ln1_b;         /* attention.output.{dense,LayerNorm} */
@@ -129,11 +144,12 @@ int ance_encoder_forward(ance_encoder_t enc, const int32_t* ids_dev, const int32
  * the executed FLOPs beside the algorithmic ones).  "ln_rows_per_warp" (1, 2 or 4; default 2, process-wide): rows a warp
  * of the LayerNorm kernel normalises side by side (bit-identical results; 2 is the fastest on B200). */
 int ance_encoder_set_param(ance_encoder_t enc, const char* name, double value);
-/* Input validation, deferred so that forward stays asynchronous: synchronises `stream` and returns
+/* Input / output validation, deferred so that forward stays asynchronous: synchronises `stream` and returns
  * ANCE_ERR_INVALID if any forward since the last check saw a token id outside [0, vocab_size) or a position
  * beyond max_position_embeddings (such lookups are clamped on the device; the reference's nn.Embedding raises
- * an index error, model/models.py:150-155 -> transformers modeling_roberta.py embeddings).  The drivers call it
- * once per encode pass. */
+ * an index error, model/models.py:150-155 -> transformers modeling_roberta.py embeddings), ANCE_ERR_UNSUPPORTED if
+ * any forward produced a non-finite embedding (fp16 range exceeded, or NaN weights).  The drivers call it once per
+ * encode pass. */
 int ance_encoder_check(ance_encoder_t enc, void* stream);
 /* Debug / parity: copy the hidden states after layer `layer` (0 = embeddings) of the last forward
  * into out_dev [B*L, hidden] fp32 (with prune_last_layer the last layer holds its B CLS rows first). */

@@ -1,5 +1,6 @@
 """world_size-2 (and 3) `gloo` runs of the sharded refresh logic on CPU: rank striding, the all-gather
-of query rows in merged order, per-shard top-k with row offsets, gather + host merge.  The local
+of query rows in merged order, per-shard top-k with row offsets, all-to-all of the lists to the rank that owns
+each query, host merge there, final gather of the merged labels.  The local
 search is the CPU oracle (test infrastructure) — the point here is the host/collective logic."""
 import os
 import socket
@@ -45,12 +46,19 @@ def _worker(rank, world, port, n_p, n_q, k, tmpdir):
             return torch.from_numpy(D), torch.from_numpy(np.where(I >= 0, I + row_offset, -1))
 
         I = drv.sharded_search(local_search, p_loc.shape[0], q_all, k, merge_threads=2)
+        # several (ragged) query blocks in flight: the all-to-all / pipelined-merge path of a 503k-query refresh in small
+        Ib = drv.sharded_search(local_search, p_loc.shape[0], q_all, k, merge_threads=1, query_block=5)
+        own_I, own_q = drv.sharded_search(local_search, p_loc.shape[0], q_all, k, query_block=7, gather_to_rank0=False)
+        _, Ig = flat_ip_oracle.search_bruteforce(P[p2id], Q[q2id], k)
+        assert (own_I == Ig[own_q]).all()          # every rank holds the merged lists of the queries it owns
+        counts = [None] * world
+        dist.all_gather_object(counts, own_q.tolist())
+        assert sorted(sum(counts, [])) == list(range(n_q))   # ... and every query is owned exactly once
         if rank == 0:
-            _, Ig = flat_ip_oracle.search_bruteforce(P[p2id], Q[q2id], k)
-            assert (I == Ig).all()
+            assert (I == Ig).all() and (Ib == Ig).all()
             np.save(os.path.join(tmpdir, "I.npy"), I)
         else:
-            assert I is None
+            assert I is None and Ib is None
         # the reference's StreamingDataset stride under an initialised process group
         lens = np.ones(n_q, dtype=np.int32)
         base = os.path.join(tmpdir, f"cache{rank}")

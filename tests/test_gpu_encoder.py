@@ -1,11 +1,13 @@
 """Parity of the sm_100a encoder with (i) the golden outputs of the reference's own classes
 (tests/golden/encoder_*.npz, fp32 HF eager) and (ii) the CPU oracle layer by layer.
 
-Tolerance (floating point, stated once): activations are stored in bf16 (8-bit significand) between
-kernels, all accumulation / LayerNorm / softmax in fp32.  Against the reference's fp32 forward on
-unit-variance outputs that gives   min cosine >= 0.9995   and   max |diff| <= 0.1   after 12 layers
-(measured on B200: cosine 0.99988, max |diff| 0.062; one bf16 rounding of a value in [4, 8) is
-already 0.0156)."""
+Tolerance (floating point, stated once; BASELINE.md par. 5): weights and activations are stored in fp16
+(11-bit significand) between kernels, all accumulation / LayerNorm / softmax in fp32.  Against the
+reference's fp32 forward on unit-variance outputs the gate is   min cosine >= 0.9995   and
+max |diff| <= 3e-2   after 12 layers, plus retrieval overlap@200 >= 0.99 against the fp32-encoded corpus
+(test_retrieval_overlap_at_200).  The bf16 storage variant (8-bit significand, selectable for checkpoints
+that overflow fp16) is held to max |diff| <= 0.1 (one bf16 rounding of a value in [4, 8) is already 0.0156)
+and its overlap is reported next to the fp16 one."""
 import os
 
 import numpy as np
@@ -15,7 +17,8 @@ import torch
 from oracle.encoder_oracle import RobertaDotOracle, random_roberta_state_dict
 
 pytestmark = pytest.mark.gpu
-COS, MAXABS = 0.9995, 0.1
+COS, MAXABS = 0.9995, 0.03
+MAXABS_BF16 = 0.1
 
 
 def _cfg():
@@ -25,11 +28,12 @@ def _cfg():
                          pad_token_id=1, bos_token_id=0, eos_token_id=2)
 
 
-def _close(a, b):
+def _close(a, b, maxabs=MAXABS):
     a, b = a.float().cpu(), torch.as_tensor(b).float()
     cos = torch.nn.functional.cosine_similarity(a, b, dim=-1).min().item()
     mx = (a - b).abs().max().item()
-    assert cos >= COS and mx <= MAXABS, f"min cosine {cos}, max abs {mx}"
+    assert cos >= COS and mx <= maxabs, f"min cosine {cos}, max abs {mx}"
+    return cos, mx
 
 
 @pytest.fixture(scope="module")
@@ -180,3 +184,99 @@ def test_layer_norm_rows_per_warp_variants_are_bit_identical(rdot):
     finally:
         enc.set_param("ln_rows_per_warp", 2)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_bf16_storage_variant_vs_reference_golden(golden_dir):
+    """operand_fmt = bf16: same kernels, 8-bit significand storage; looser max-abs (stated at the top)."""
+    from ance_b200.models import RobertaDot_NLL_LN
+    m = RobertaDot_NLL_LN(_cfg())
+    m.load_state_dict(random_roberta_state_dict(seed=0), strict=True)
+    m.encoder_operand = "bf16"
+    m = m.cuda().eval()
+    g = np.load(os.path.join(golden_dir, "encoder_rdot_nll.npz"))
+    emb = m.encode_lens(torch.from_numpy(g["ids"]).cuda(), torch.from_numpy(g["lens"]).cuda())
+    _close(emb, g["emb"], MAXABS_BF16)
+    assert m._encoder(torch.device("cuda", torch.cuda.current_device())).operand == "bf16"
+
+
+def test_fp16_overflow_is_reported_not_silent():
+    """A checkpoint whose activations leave the fp16 range gives inf/NaN embeddings: check_inputs() must raise and
+    point at bf16, and the bf16 variant must encode the same checkpoint finitely."""
+    from ance_b200._lib import AnceError
+    from ance_b200.models import RobertaDot_NLL_LN
+    sd = random_roberta_state_dict(seed=1, n_layer=2)
+    sd["roberta.encoder.layer.0.intermediate.dense.bias"] = sd["roberta.encoder.layer.0.intermediate.dense.bias"] + 1.0e5
+    cfg = _cfg()
+    cfg.num_hidden_layers = 2
+    ids = torch.randint(3, 50265, (4, 64), dtype=torch.int32, device="cuda")
+    lens = torch.full((4,), 64, dtype=torch.int32, device="cuda")
+    for operand, ok in (("fp16", False), ("bf16", True)):
+        m = RobertaDot_NLL_LN(cfg)
+        m.load_state_dict(sd, strict=True)
+        m.encoder_operand = operand
+        m = m.cuda().eval()
+        emb = m.encode_lens(ids, lens)
+        if ok:
+            m.check_inputs()
+            assert torch.isfinite(emb).all()
+        else:
+            with pytest.raises(AnceError, match="fp16 range"):
+                m.check_inputs()
+
+
+def test_retrieval_overlap_at_200(rdot):
+    """BASELINE.md par. 5's second encoder gate: encode a 20,480-passage / 512-query 12-layer fixture with the sm_100a
+    encoder and with the fp32 oracle, run the ORACLE search (exact fp32 inner product, top-200) on both embedding sets
+    and compare the neighbour sets the trainer would consume.  The fp32 side is oracle.encoder_oracle placed on the GPU
+    (plain fp32, TF32 off) and tied to its CPU run on a slice."""
+    import json
+    from oracle import flat_ip_oracle
+    model, sd = rdot
+    rng = np.random.default_rng(11)
+    n_p, n_q, k = 20480, 512, 200
+
+    def synth(n, L, mean, sdv, lo):
+        lens = np.clip(rng.normal(mean, sdv, size=n).round().astype(np.int32), lo, L)
+        ids = rng.integers(3, 50265, size=(n, L)).astype(np.int32)
+        ids[np.arange(L)[None, :] >= lens[:, None]] = 1
+        ids[:, 0] = 0
+        ids[np.arange(n), lens - 1] = 2
+        return ids, lens
+
+    p_ids, p_lens = synth(n_p, 128, 76, 28, 8)
+    q_ids, q_lens = synth(n_q, 64, 9, 3, 4)
+    orc_gpu = RobertaDotOracle(sd, device="cuda")
+
+    def oracle_encode(ids, lens, bs=512):
+        out = []
+        for s in range(0, ids.shape[0], bs):
+            m = np.arange(ids.shape[1])[None, :] < lens[s:s + bs, None]
+            out.append(orc_gpu.body_emb(torch.from_numpy(ids[s:s + bs]), torch.from_numpy(m)).cpu())
+        return torch.cat(out).numpy()
+
+    P_ref, Q_ref = oracle_encode(p_ids, p_lens), oracle_encode(q_ids, q_lens)
+    # the GPU-placed fp32 oracle is the CPU oracle up to fp32 summation order
+    cpu = RobertaDotOracle(sd).body_emb(torch.from_numpy(p_ids[:16]), torch.from_numpy(np.arange(128)[None, :] < p_lens[:16, None]))
+    assert np.abs(cpu.numpy() - P_ref[:16]).max() <= 2e-4
+    _, I_ref = flat_ip_oracle.search(P_ref, Q_ref, k)
+    report = {"n_passages": n_p, "n_queries": n_q, "k": k}
+    for operand in ("fp16", "bf16"):
+        model.encoder_operand = operand
+        try:
+            P = model.encode_lens(torch.from_numpy(p_ids).cuda(), torch.from_numpy(p_lens).cuda()).cpu().numpy()
+            Q = model.encode_lens(torch.from_numpy(q_ids).cuda(), torch.from_numpy(q_lens).cuda()).cpu().numpy()
+        finally:
+            model.encoder_operand = "fp16"
+        _, I = flat_ip_oracle.search(P, Q, k)
+        overlap = float(np.mean([len(np.intersect1d(I[i], I_ref[i])) for i in range(n_q)])) / k
+        top10 = float(np.mean([len(np.intersect1d(I[i, :10], I_ref[i, :10])) for i in range(n_q)])) / 10
+        cos = float((P * P_ref).sum(1).min() / 768.0)
+        report[operand] = {"overlap_at_200": overlap, "overlap_at_10": top10,
+                           "max_abs": float(np.abs(P - P_ref).max()), "rms": float(np.sqrt(np.mean((P - P_ref) ** 2)))}
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        json.dump(report, open(os.path.join(out_dir, "overlap_at_200.json"), "w"), indent=1)
+    print("retrieval overlap:", json.dumps(report))
+    assert report["fp16"]["max_abs"] <= MAXABS, report
+    assert report["fp16"]["overlap_at_200"] >= 0.99, report
+    assert report["bf16"]["max_abs"] <= MAXABS_BF16, report
