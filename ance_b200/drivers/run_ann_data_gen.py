@@ -389,15 +389,26 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
                      latest_step_num, backend=None):
     """run_ann_data_gen.py:231-336."""
     t_start = time.time()
+    detail: Dict[str, float] = {}
+
+    def lap(name, t0):
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        detail[name] = time.time() - t0
+        return time.time()
+
     if backend is None:
         _, _, model = load_model(args, checkpoint_path)
         backend = B200Backend(args, model)
     step = str(latest_step_num)
 
+    t = time.time()
     logger.info("***** inference of dev query *****")
     dev_emb, dev_ids = backend.encode(os.path.join(args.data_dir, "dev-query"), True)
+    t = lap("encode_dev_query_s", t)
     logger.info("***** inference of passages *****")
     index, p_emb, p_ids = backend.encode(os.path.join(args.data_dir, "passages"), False, build_index=True)
+    t = lap("encode_passages_s", t)
     logger.info("***** Done passage inference *****")
     if args.inference:
         _dump(args, "dev_query_" + step + "_", dev_emb, dev_ids)
@@ -405,6 +416,7 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
         return None
     logger.info("***** inference of train query *****")
     q_emb, q_ids = backend.encode(os.path.join(args.data_dir, "train-query"), True)
+    t = lap("encode_train_query_s", t)
     t_enc = time.time()
 
     device = p_emb.device
@@ -412,12 +424,15 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
     passage_embedding2id = all_gather_ids(p_ids, device)
     dev_all, dev_query_embedding2id = all_gather_rows(dev_emb), all_gather_ids(dev_ids, device)
     q_all, query_embedding2id = all_gather_rows(q_emb), all_gather_ids(q_ids, device)
+    t = lap("all_gather_s", t)
 
     dev_I = sharded_search(local_search, p_emb.shape[0], dev_all, 100)               # run_ann_data_gen.py:276
+    t = lap("search_dev_s", t)
     q_start, q_end = postprocess.query_chunk(q_all.shape[0], output_num, args.ann_chunk_factor)
     q_all, query_embedding2id = q_all[q_start:q_end], query_embedding2id[q_start:q_end]
     logger.info("Chunked {} query from {}".format(q_end - q_start, q_emb.shape[0]))
     I = sharded_search(local_search, p_emb.shape[0], q_all.contiguous(), args.topk_training)  # :303
+    t = lap("search_train_s", t)
     t_search = time.time()
     if not is_first_worker():
         return None
@@ -425,20 +440,23 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
     dev_ndcg, num_queries_dev = postprocess.eval_dev_query(dev_query_embedding2id, passage_embedding2id,
                                                            dev_query_positive_id, dev_I)
     print("Rank:" + str(getattr(args, "rank", 0)) + " --- ANN NDCG@10:" + str(dev_ndcg))
+    t = lap("post_ndcg_s", t)
     sampler = "reference" if args.reference_sampling else "fast"
     negatives, mrr, nq = postprocess.generate_negatives(
         query_embedding2id, passage_embedding2id, training_query_positive_id, I, args.negative_sample,
         select_topk=args.ann_measure_topk_mrr, sampler=sampler, seed=args.seed)
     if args.ann_measure_topk_mrr:
         print("Rank:" + str(getattr(args, "rank", 0)) + " --- ANN MRR:" + str(mrr / max(nq, 1)))
+    t = lap("post_negatives_s", t)
     logger.info("***** Construct ANN Triplet *****")
     os.makedirs(args.output_dir, exist_ok=True)
     postprocess.write_training_data(os.path.join(args.output_dir, "ann_training_data_" + str(output_num)),
                                     query_embedding2id, training_query_positive_id, negatives, sampler=sampler,
                                     seed=args.seed)
     postprocess.write_ndcg(os.path.join(args.output_dir, "ann_ndcg_" + str(output_num)), dev_ndcg, checkpoint_path)
+    lap("post_write_s", t)
     args.last_refresh_timing = {"encode_s": t_enc - t_start, "search_s": t_search - t_enc, "post_s": time.time() - t_search,
-                                "search_stats": backend.index.stats() if hasattr(backend, "index") else None}
+                                "detail": detail, "search_stats": index.stats() if index.ntotal else None}
     logger.info("refresh %d: encode %.1fs search %.1fs post %.1fs", output_num, t_enc - t_start, t_search - t_enc,
                 time.time() - t_search)
     return dev_ndcg, num_queries_dev

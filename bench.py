@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py — ANN-refresh throughput (BASELINE.json metric) on N GPUs of one node.
 
-One STEP = one slice of a full refresh at the refresh's own passage:query mix (8,841,823 : 502,939 = 17.6:1; the step uses 16:1):
-    encode PB passages (rdot_nll, RoBERTa-base, L=128, full-length synthetic token ids)
-  + encode QB train queries (L=64)
-  + top-200 inner-product search of those QB queries against the resident 8,841,823 x 768 index
-    (synthetic LayerNorm-like clustered rows; sharded i % N across ranks when N > 1,
-    queries all-gathered, per-shard top-200 merged on rank 0).
-value = (passages encoded + queries searched) per second, whole job.  `stages` breaks it down into
-the two rates the metric names (passages encoded/s, queries top-200/s).
+One STEP = one slice of a full refresh at (about) the refresh's own passage:query mix, through the code the drop-in driver
+runs (ance_b200.drivers.run_ann_data_gen):
+    encode PB passages into index row storage and add them in place (quantisation + norms: `IndexFlatIP.add`)
+  + encode QB train queries
+  + top-k inner-product search of those queries against the RESIDENT full-size index (sharded i % N across ranks when
+    N > 1: queries all-gathered, per-shard top-k, all-to-all of the lists to the rank that owns each query, host k-way merge
+    there, merged labels gathered on rank 0 — `sharded_search`, the driver's own function).
+value = (passages encoded + queries searched) per second, whole job; `stages` gives the two rates the metric names.
+
+Workloads (--workload; the default is the one BASELINE.json's metric is quoted on):
+  marco_psg        BASELINE configs[1]: rdot_nll RoBERTa-base, passages L=128, queries L=64, 8,841,823 x 768 index, top-200
+  marco_doc_maxp   configs[3]: rdot_nll_multi_chunk, documents 2048 = 4 x 512 chunks, 12,855,340 x 768 chunk-row index, top-200
+  dpr              configs[4]: DPR BiEncoder (BERT-base, CLS, no head), L=256, 21,015,324 x 768 un-normalised rows, top-100
 
   python bench.py --gpus 1 --steps 5 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
          bench.py --gpus N --steps K --warmup W
-  python bench.py --impl reference ...     # the reference's CPU arithmetic (oracle port) on the host cores
+  python bench.py --impl reference ...     # the reference's CPU arithmetic on the host cores (see run_reference)
 """
 from __future__ import annotations
 
@@ -31,24 +36,39 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_PASSAGES = 8841823
-N_QUERIES = 502939
 DIM = 768
-L_P, L_Q, TOPK = 128, 64, 200
-METRIC = "ANN-refresh throughput: passages encoded/sec + queries top-200/sec, 8.8M x 768"
-UNIT = "passages+queries/s"
-FLOP_SEQ = lambda L: 12 * (24 * 768 * 768 * L + 4 * 768 * L * L) + 2 * 768 * 768
-GEMM_FLOP_SEQ = lambda L: 12 * 24 * 768 * 768 * L + 2 * 768 * 768               # the GEMM kernel's share
-# Last-layer pruning: out-proj + FFN of the last layer run on the CLS row only (result-identical), so
-# 18 * 768^2 * (L - 1) FLOP per sequence are NOT executed.  Fractions of peak are computed from EXECUTED flops.
-PRUNED_FLOP_SEQ = lambda L: 18 * 768 * 768 * (L - 1)
+WORKLOADS = {
+    "marco_psg": dict(
+        title="BASELINE configs[1]: MS MARCO passage 8.8M, rdot_nll seq_len=128, encode + top-200",
+        metric="ANN-refresh throughput: passages encoded/sec + queries top-200/sec, 8.8M x 768",
+        unit="passages+queries/s", model="rdot_nll", L_p=128, L_q=64, chunks=1, n_index=8841823, topk=200,
+        pb=37888, qb=2368, index_kind="layernorm_clustered", head=True),
+    "marco_doc_maxp": dict(
+        title="BASELINE configs[3]: MS MARCO document 3.2M, rdot_nll_multi_chunk (MaxP) seq_len=2048 = 4 x 512, encode + top-200 "
+              "over 12,855,340 chunk rows",
+        metric="ANN-refresh throughput: documents (4 x 512 tokens) encoded/sec + queries top-200/sec, 12.9M x 768",
+        unit="documents+queries/s", model="rdot_nll_multi_chunk", L_p=2048, L_q=64, chunks=4, n_index=12855340, topk=200,
+        pb=2368, qb=296, index_kind="layernorm_clustered", head=True),
+    "dpr": dict(
+        title="BASELINE configs[4]: DPR 21M Wikipedia passages, BiEncoder (BERT-base CLS) seq_len=256, encode + top-100",
+        metric="ANN-refresh throughput: passages encoded/sec + queries top-100/sec, 21M x 768",
+        unit="passages+queries/s", model="dpr", L_p=256, L_q=256, chunks=1, n_index=21015324, topk=100,
+        pb=18944, qb=296, index_kind="dpr", head=False),
+}
 
 
-def roberta_cfg():
-    from transformers import RobertaConfig
-    return RobertaConfig(vocab_size=50265, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
-                         intermediate_size=3072, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5,
-                         pad_token_id=1, bos_token_id=0, eos_token_id=2)
+def flop_seq(L, head=True):          # dense, padded to L
+    return 12 * (24 * 768 * 768 * L + 4 * 768 * L * L) + (2 * 768 * 768 if head else 0)
+
+
+def gemm_flop_seq(L, head=True):     # the GEMM kernel's share
+    return 12 * 24 * 768 * 768 * L + (2 * 768 * 768 if head else 0)
+
+
+def pruned_flop_seq(L):
+    """Last-layer pruning: out-proj + FFN of the last layer run on the CLS row only (result-identical), so
+    18 * 768^2 * (L - 1) FLOP per sequence are NOT executed.  Fractions of peak are computed from EXECUTED flops."""
+    return 18 * 768 * 768 * (L - 1)
 
 
 def peaks():
@@ -56,7 +76,7 @@ def peaks():
     if os.path.exists(p):
         j = json.load(open(p))
         return {"bf16_tflops": j.get("bf16_tflops_sustained", j.get("bf16_tflops")), "hbm_gbs": j.get("hbm_gbs"),
-                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained)"}
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: the kernel is timed inside a long step)"}
     return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md, sustained)"}
 
 
@@ -93,129 +113,212 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-_ORC = None
+def workload_config(args, wl, world):
+    return {"workload": wl["title"], "index_rows": wl["n_index"], "dim": DIM, "topk": wl["topk"],
+            "passages_per_step_per_gpu": args.passages_per_step, "queries_per_step_per_gpu": args.queries_per_step,
+            "passage_len": wl["L_p"], "query_len": wl["L_q"],
+            "parallelism": ("rows i%%%d per rank, all-gather queries, all-to-all of per-shard top-k, per-rank host merge" % world)
+            if world > 1 else "single GPU",
+            "search_operand": args.search_operand, "encoder_operand": args.encoder_operand,
+            "l2": "inputs larger than L2 (16-bit index operands %.1f GB + fp32 rows %.1f GB; ~0.9 GB of activations per "
+                  "encoder pass)" % (wl["n_index"] * DIM * 2 / 1e9 / world, wl["n_index"] * DIM * 4 / 1e9 / world)}
 
 
 # =============================================================================================
-# reference arm / CPU baseline: the reference's arithmetic (oracle port) on the host cores
+# reference arm / CPU baseline: the reference's own CPU path on the host cores
+#   encode: HF-RoBERTa/BERT eager fp32 arithmetic, batch 16 (commands/run_ann_data_gen.sh) — oracle/encoder_oracle.py,
+#           pinned by golden vectors generated from the reference's classes
+#   search: faiss.IndexFlatIP when a faiss wheel is importable on the box (BASELINE.md par. 4.2), else its arithmetic
+#           restated as BASELINE.md specifies: blocked fp32 sgemm (torch.matmul -> MKL) + exact top-k, with all host
+#           cores and with the 16 threads the reference pins (run_ann_data_gen.py:269) — the faster of the two is reported
 # =============================================================================================
-_SEARCH_SAMPLE = {}
+_CPU = {}
 
 
-def cpu_step_sample(threads, n_p=32, n_q=16, search_q=64, search_rows=262144):
-    """Time a bounded sample of one step on the CPU and extrapolate to the step's unit counts.
-    Returns (passages/s, query-encodes/s, search queries/s at N = 8,841,823, seconds spent)."""
-    from oracle import flat_ip_oracle
-    from oracle.encoder_oracle import RobertaDotOracle, random_roberta_state_dict
+def _cpu_models(wl):
+    key = wl["model"]
+    if key not in _CPU:
+        from ance_b200.synthetic import random_roberta_state_dict
+        from oracle.encoder_oracle import BiEncoderOracle, RobertaDotOracle
+        if wl["model"] == "dpr":
+            sd = {**random_roberta_state_dict(seed=0, vocab=30522, max_pos=512, head=False, prefix="question_model."),
+                  **random_roberta_state_dict(seed=1, vocab=30522, max_pos=512, head=False, prefix="ctx_model.")}
+            _CPU[key] = BiEncoderOracle(sd)
+        else:
+            _CPU[key] = RobertaDotOracle(random_roberta_state_dict(seed=0))
+    return _CPU[key]
+
+
+def synth_tokens(n, L, seed, wl):
+    """Full-length synthetic token ids (the roofline regime): int32 [n, L], position 0 = <s>/[CLS]."""
+    g = torch.Generator().manual_seed(seed)
+    hi = 30522 if wl["model"] == "dpr" else 50265
+    ids = torch.randint(3, hi, (n, L), generator=g, dtype=torch.int32)
+    ids[:, 0] = 101 if wl["model"] == "dpr" else 0
+    return ids
+
+
+def cpu_search_topk(P: torch.Tensor, Q: torch.Tensor, k: int, threads: int, p_block: int = 65536):
+    """Blocked fp32 sgemm + exact top-k with a running merge (the faiss IndexFlatIP arithmetic)."""
     torch.set_num_threads(threads)
-    global _ORC
-    if _ORC is None:
-        _ORC = RobertaDotOracle(random_roberta_state_dict(seed=0))  # weights: setup, not timed
-    orc = _ORC
+    best_d = torch.full((Q.shape[0], k), -float("inf"))
+    best_i = torch.full((Q.shape[0], k), -1, dtype=torch.int64)
+    for s in range(0, P.shape[0], p_block):
+        S = Q @ P[s:s + p_block].T
+        d, i = torch.topk(S, min(k, S.shape[1]), dim=1)
+        d, i = torch.cat([best_d, d], 1), torch.cat([best_i, i + s], 1)
+        best_d, sel = torch.topk(d, k, dim=1)
+        best_i = torch.gather(i, 1, sel)
+    return best_d, best_i
+
+
+def cpu_step_sample(wl, n_p, n_q, search_q, search_rows, want_outputs=False):
+    """Time a bounded sample of one step on the CPU.  Returns rates (units/s; the search rate is scaled linearly in the
+    row count to the workload's index size), what was used, and optionally the sample's inputs / outputs for the
+    parity block of the B200 arm."""
+    cores = os.cpu_count() or 1
+    thread_sets = sorted({cores, min(cores, 16)}, reverse=True)
+    orc = _cpu_models(wl)
     t_all = time.time()
-    g = torch.Generator().manual_seed(0)
-    ids = torch.randint(3, 50265, (n_p, L_P), generator=g)
-    orc.body_emb(ids[:2], torch.ones_like(ids[:2]))  # warm-up
-    t0 = time.time()
-    for s in range(0, n_p, 16):  # the reference's per_gpu_eval_batch_size in the shipped scripts
-        orc.body_emb(ids[s:s + 16], torch.ones_like(ids[s:s + 16]))
-    rate_p = n_p / (time.time() - t0)
-    qids = torch.randint(3, 50265, (n_q, L_Q), generator=g)
-    t0 = time.time()
-    orc.query_emb(qids, torch.ones_like(qids))
-    rate_q = n_q / (time.time() - t0)
-    key = (search_rows, search_q)
-    if key not in _SEARCH_SAMPLE:   # synthetic operands: setup, generated once per process, not timed
-        rng = np.random.default_rng(0)
-        _SEARCH_SAMPLE.clear()
-        _SEARCH_SAMPLE[key] = (rng.standard_normal((search_rows, DIM), dtype=np.float32),
-                               rng.standard_normal((search_q, DIM), dtype=np.float32))
-    P, Q = _SEARCH_SAMPLE[key]
-    t0 = time.time()
-    flat_ip_oracle.search(P, Q, TOPK, slack=64, q_block=search_q, p_block=65536)
-    qps_slice = search_q / (time.time() - t0)
-    qps_full = qps_slice * search_rows / N_PASSAGES
-    return rate_p, rate_q, qps_full, time.time() - t_all
+    L_p, L_q, C = wl["L_p"], wl["L_q"], wl["chunks"]
+    p_ids, q_ids = synth_tokens(n_p, L_p, 11, wl), synth_tokens(n_q, L_q, 12, wl)
+
+    def enc_p(ids):
+        m = torch.ones_like(ids)
+        return orc.body_emb_multi_chunk(ids, m) if C > 1 else orc.body_emb(ids, m)
+
+    best = None
+    for th in thread_sets:
+        torch.set_num_threads(th)
+        enc_p(p_ids[:1])  # warm-up
+        t0 = time.time()
+        outs = [enc_p(p_ids[s:s + 16]) for s in range(0, n_p, 16)]   # per_gpu_eval_batch_size of the shipped scripts
+        rp = n_p / (time.time() - t0)
+        t0 = time.time()
+        qo = orc.query_emb(q_ids, torch.ones_like(q_ids))
+        rq = n_q / (time.time() - t0)
+        if best is None or rp > best[0]:
+            best = (rp, rq, th, torch.cat(outs), qo)
+    rate_p, rate_q, enc_threads, p_emb, q_emb = best
+    key = (search_rows, search_q, wl["index_kind"])
+    if _CPU.get("search_key") != key:   # synthetic operands: setup, generated once per process, not timed
+        g = torch.Generator().manual_seed(0)
+        P = torch.randn(search_rows, DIM, generator=g)
+        Qs = torch.randn(search_q, DIM, generator=g)
+        if wl["index_kind"] != "dpr":
+            P = (P - P.mean(1, keepdim=True)) / P.std(1, keepdim=True, unbiased=False)
+            Qs = (Qs - Qs.mean(1, keepdim=True)) / Qs.std(1, keepdim=True, unbiased=False)
+        _CPU["search_key"], _CPU["search_ops"] = key, (P.contiguous(), Qs.contiguous())
+    P, Qs = _CPU["search_ops"]
+    k = wl["topk"]
+    search_kind, qps_slice, s_threads, D_cpu, I_cpu = None, 0.0, None, None, None
+    try:
+        import faiss  # noqa: F401  (absent from this image; used when the box has it)
+        for th in thread_sets:
+            faiss.omp_set_num_threads(th)
+            index = faiss.IndexFlatIP(DIM)
+            index.add(P.numpy())
+            t0 = time.time()
+            D_np, I_np = index.search(Qs.numpy(), k)
+            q = search_q / (time.time() - t0)
+            if q > qps_slice:
+                search_kind, qps_slice, s_threads = "faiss.IndexFlatIP", q, th
+                D_cpu, I_cpu = torch.from_numpy(D_np), torch.from_numpy(I_np)
+    except ImportError:
+        for th in thread_sets:
+            t0 = time.time()
+            d, i = cpu_search_topk(P, Qs, k, th)
+            q = search_q / (time.time() - t0)
+            if q > qps_slice:
+                search_kind, qps_slice, s_threads, D_cpu, I_cpu = "blocked fp32 sgemm (MKL) + top-k", q, th, d, i
+    qps_full = qps_slice * search_rows / wl["n_index"]
+    info = {"rate_p": rate_p, "rate_q": rate_q, "qps_full": qps_full, "seconds": time.time() - t_all,
+            "encode_threads": enc_threads, "search_threads": s_threads, "search_kind": search_kind, "host_cores": cores}
+    if want_outputs:
+        info["outputs"] = dict(p_ids=p_ids, q_ids=q_ids, p_emb=p_emb, q_emb=q_emb, P=P, Q=Qs, D=D_cpu, I=I_cpu)
+    return info
 
 
-# bounded samples of one step for the CPU arm: ~15 s of host work inside the default bench run, ~8 s per step of
+# bounded samples of one step for the CPU arm: ~15-25 s of host work inside the default bench run, a few s per step of
 # `--impl reference` (K + W steps must end within a few minutes)
-CPU_BASELINE_SAMPLE = dict(n_p=192, n_q=48, search_q=128, search_rows=524288)
-REF_STEP_SAMPLE = dict(n_p=96, n_q=24, search_q=64, search_rows=524288)
-if os.environ.get("ANCE_BENCH_TINY_CPU"):   # contract tests only (tests/test_bench_contract.py)
-    CPU_BASELINE_SAMPLE = REF_STEP_SAMPLE = dict(n_p=2, n_q=2, search_q=4, search_rows=4096)
+def cpu_samples(wl):
+    n_p = {"marco_psg": 192, "marco_doc_maxp": 16, "dpr": 96}[wl_name(wl)]
+    base = dict(n_p=n_p, n_q=48, search_q=1024, search_rows=1 << 20)
+    ref = dict(n_p=max(16, n_p // 2), n_q=32, search_q=512, search_rows=1 << 19)
+    if os.environ.get("ANCE_BENCH_TINY_CPU"):   # contract tests only (tests/test_bench_contract.py)
+        base = ref = dict(n_p=2, n_q=2, search_q=4, search_rows=4096)
+    return base, ref
 
 
-def sample_text(sm):
-    return ("%d passages L=%d + %d queries L=%d through the oracle port of the reference's HF-RoBERTa eager fp32 path (batch 16); "
-            "%d queries x %s rows blocked fp32 sgemm + top-%d (faiss IndexFlatIP arithmetic), scaled linearly to N=%s"
-            % (sm["n_p"], L_P, sm["n_q"], L_Q, sm["search_q"], format(sm["search_rows"], ","), TOPK, format(N_PASSAGES, ",")))
+def wl_name(wl):
+    return next(k for k, v in WORKLOADS.items() if v is wl)
 
 
-def cpu_threads():
-    """The reference pins its CPU search to 16 OpenMP threads (run_ann_data_gen.py:269); small-batch fp32
-    matmuls stop scaling (and regress) far below the 128+ hardware threads of a B200 host."""
-    return min(os.cpu_count() or 1, 16)
+def sample_text(wl, sm, info):
+    return ("%d %s L=%d + %d queries L=%d through the oracle port of the reference's HF eager fp32 path (batch 16, %d threads); "
+            "%d queries x %s rows %s (%d threads), top-%d, scaled linearly to N=%s; host has %d cores"
+            % (sm["n_p"], "documents" if wl["chunks"] > 1 else "passages", wl["L_p"], sm["n_q"], wl["L_q"],
+               info["encode_threads"], sm["search_q"], format(sm["search_rows"], ","), info["search_kind"],
+               info["search_threads"], wl["topk"], format(wl["n_index"], ","), info["host_cores"]))
 
 
-def cpu_value(pb, qb, rate_p, rate_q, qps_full):
-    t = pb / rate_p + qb / rate_q + qb / qps_full
+def cpu_value(pb, qb, info):
+    t = pb / info["rate_p"] + qb / info["rate_q"] + qb / info["qps_full"]
     return (pb + qb) / t
 
 
-def run_reference(args):
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = cpu_threads()
     pb, qb = args.passages_per_step, args.queries_per_step
-    vals, spent = [], 0.0
+    _, ref_sample = cpu_samples(wl)
+    vals, spent, info = [], 0.0, None
     for i in range(args.warmup + args.steps):
-        rate_p, rate_q, qps, dt = cpu_step_sample(threads, **REF_STEP_SAMPLE)
-        spent += dt
+        info = cpu_step_sample(wl, **ref_sample)
+        spent += info["seconds"]
         if i >= args.warmup:
-            vals.append(cpu_value(pb, qb, rate_p, rate_q, qps))
+            vals.append(cpu_value(pb, qb, info))
     v = float(np.mean(vals))
-    sample = "per step: " + sample_text(REF_STEP_SAMPLE) + "; extrapolated to the step's %d passages + %d queries; %.0f s of CPU work per step" % (
+    sample = "per step: " + sample_text(wl, ref_sample, info) + "; extrapolated to the step's %d + %d units; %.1f s of CPU work per step" % (
         pb, qb, spent / max(1, args.warmup + args.steps))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": (pb + qb) / v * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(args, wl, 1),
+        "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": max(info["encode_threads"], info["search_threads"]),
+                         "kind": "port", "sample": sample, "passages_per_s": info["rate_p"],
+                         "queries_topk_per_s": info["qps_full"]},
+        "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
-
-
-def workload_config(args, world):
-    return {"workload": "BASELINE configs[1]: MS MARCO passage 8.8M, rdot_nll seq_len=128, encode + top-200",
-            "index_rows": N_PASSAGES, "dim": DIM, "topk": TOPK, "passages_per_step_per_gpu": args.passages_per_step,
-            "queries_per_step_per_gpu": args.queries_per_step, "passage_len": L_P, "query_len": L_Q,
-            "parallelism": "rows i%%%d per rank, all-gather queries, host merge" % world if world > 1 else "single GPU",
-            "search_operand": args.search_operand,
-            "l2": "inputs larger than L2 (index 13.6 GB 16-bit + 27 GB fp32; ~0.7 GB of activations per encoder pass)"}
 
 
 # =============================================================================================
 # B200 arm
 # =============================================================================================
-def synth_index_rows(n, dev, seed, cent):
-    g = torch.Generator(device=dev).manual_seed(seed)
-    for s in range(0, n, 1 << 20):
-        e = min(n, s + (1 << 20))
-        x = 0.5 * torch.randn(e - s, DIM, device=dev, generator=g) + \
-            0.5 * cent[torch.randint(0, cent.shape[0], (e - s,), device=dev, generator=g)]
-        yield (x - x.mean(1, keepdim=True)) / x.std(1, keepdim=True, unbiased=False)
+def build_model(wl, dev, encoder_operand):
+    from ance_b200.models import BiEncoder, RobertaDot_CLF_ANN_NLL_MultiChunk, RobertaDot_NLL_LN
+    from ance_b200.synthetic import random_roberta_state_dict, roberta_base_config
+    if wl["model"] == "dpr":
+        model = BiEncoder()
+        model.load_state_dict({**random_roberta_state_dict(seed=0, vocab=30522, max_pos=512, head=False, prefix="question_model."),
+                               **random_roberta_state_dict(seed=1, vocab=30522, max_pos=512, head=False, prefix="ctx_model.")})
+    else:
+        cls = RobertaDot_CLF_ANN_NLL_MultiChunk if wl["model"] == "rdot_nll_multi_chunk" else RobertaDot_NLL_LN
+        model = cls(roberta_base_config())
+        model.load_state_dict(random_roberta_state_dict(seed=0), strict=True)
+    model.encoder_operand = encoder_operand
+    return model.to(dev).eval()
 
 
-def run_b200(args):
+def run_b200(args, wl):
     import torch.distributed as dist
     from ance_b200 import _lib
-    from ance_b200.models import RobertaDot_NLL_LN
-    from ance_b200.search import IndexFlatIP, merge_topk_host
-    from oracle.encoder_oracle import random_roberta_state_dict  # seeded synthetic weights only (no oracle compute)
+    from ance_b200.drivers.run_ann_data_gen import sharded_search
+    from ance_b200.search import IndexFlatIP
+    from ance_b200.synthetic import synth_index_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -227,63 +330,69 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl")
     pb, qb = args.passages_per_step, args.queries_per_step
+    L_p, L_q, C, k = wl["L_p"], wl["L_q"], wl["chunks"], wl["topk"]
+    Lc = L_p // C                                  # tokens per encoded sequence
+    model = build_model(wl, dev, args.encoder_operand)
+    mask_form = wl["model"] == "dpr"               # DPR: mask = ids != 0 (DPR_data.py:283); MARCO: lengths (msmarco_data.py:282)
 
-    model = RobertaDot_NLL_LN(roberta_cfg())
-    model.load_state_dict(random_roberta_state_dict(seed=0), strict=True)
-    model = model.to(dev).eval()
-    # this rank's shard of the synthetic corpus
-    n_local = len(range(rank, N_PASSAGES, world))
-    offset = sum(len(range(r, N_PASSAGES, world)) for r in range(rank))
+    # this rank's shard of the synthetic corpus, resident for the whole run
+    n_index = wl["n_index"]
+    n_local = len(range(rank, n_index, world))
     index = IndexFlatIP(DIM, capacity=n_local, device=dev, operand=args.search_operand)
-    cent = torch.randn(1024, DIM, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
-    for x in synth_index_rows(n_local, dev, 1234 + rank, cent):
+    for x in synth_index_rows(n_local, DIM, dev, 1234 + rank, wl["index_kind"]):
         index.add(x)
     del x
     torch.cuda.empty_cache()
+    # the step's own passages go into a scratch index of pb * C rows (in-place add, as the driver does)
+    step_rows = torch.empty((pb * C, DIM), dtype=torch.float32, device=dev)
+    step_index = IndexFlatIP(DIM, device=dev, operand=args.search_operand, storage=step_rows)
 
-    # synthetic token ids: HOST pinned (e2e) and device-resident copies (value)
-    g = torch.Generator().manual_seed(100 + rank)
-    p_ids_h = torch.randint(3, 50265, (pb, L_P), generator=g, dtype=torch.int32).pin_memory()
-    q_ids_h = torch.randint(3, 50265, (qb, L_Q), generator=g, dtype=torch.int32).pin_memory()
-    p_ids_h[:, 0], q_ids_h[:, 0] = 0, 0
-    p_len_h = torch.full((pb,), L_P, dtype=torch.int32).pin_memory()
-    q_len_h = torch.full((qb,), L_Q, dtype=torch.int32).pin_memory()
-    p_ids_d, q_ids_d, p_len_d, q_len_d = (t.to(dev) for t in (p_ids_h, q_ids_h, p_len_h, q_len_h))
-    D_h = torch.empty((qb * world, TOPK), dtype=torch.float32).pin_memory()
-    I_h = torch.empty((qb * world, TOPK), dtype=torch.int64).pin_memory()
+    # synthetic token ids: HOST pinned (e2e) and device-resident copies (value); full length = the roofline regime
+    p_ids_h = synth_tokens(pb, L_p, 100 + rank, wl).pin_memory()
+    q_ids_h = synth_tokens(qb, L_q, 200 + rank, wl).pin_memory()
+    p_mask_h = torch.ones((pb, L_p), dtype=torch.bool).pin_memory()     # GetProcessingFn's attention_mask (bool [L])
+    q_mask_h = torch.ones((qb, L_q), dtype=torch.bool).pin_memory()
+    p_ids_d, q_ids_d = p_ids_h.to(dev), q_ids_h.to(dev)
+    p_len_d = torch.full((pb,), L_p, dtype=torch.int32, device=dev)
+    q_len_d = torch.full((qb,), L_q, dtype=torch.int32, device=dev)
+    local_search = lambda q, kk, off: index.search_device(q, kk, row_offset=off)   # noqa: E731
 
-    def step(host: bool):
-        if host:
-            pi, pl = p_ids_h.to(dev, non_blocking=True), p_len_h.to(dev, non_blocking=True)
-            qi, ql = q_ids_h.to(dev, non_blocking=True), q_len_h.to(dev, non_blocking=True)
+    def encode_passages_fast(ids, lens):
+        """device-resident inputs, the refresher's fast path (lengths instead of masks, rows written in place)"""
+        if wl["model"] == "dpr":
+            step_rows.copy_(model.body_emb(ids, ids != 0))
+        elif C > 1:
+            step_rows.copy_(model.encode_lens_multi_chunk(ids, lens).reshape(pb * C, DIM))
         else:
-            pi, pl, qi, ql = p_ids_d, p_len_d, q_ids_d, q_len_d
-        model.encode_lens(pi, pl)               # passages of this slice (rows stay in HBM)
-        q = model.encode_lens(qi, ql)
+            model.encode_lens(ids, lens, out=step_rows)
+
+    def step_value():
+        step_index.reset()
+        encode_passages_fast(p_ids_d, p_len_d)
+        step_index.add(step_rows)
+        q = model.query_emb(q_ids_d, q_ids_d != 0) if mask_form else model.encode_lens(q_ids_d, q_len_d)
         if world > 1:
             q_all = torch.empty((qb * world, DIM), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(q_all, q.contiguous())
         else:
             q_all = q
-        D, I = index.search_device(q_all.contiguous(), TOPK, row_offset=offset)
+        return sharded_search(local_search, n_local, q_all.contiguous(), k)    # numpy labels on rank 0
+
+    def step_e2e():
+        """The calls a user of the reference makes (run_ann_data_gen.py:172-180,269-303), host buffers in, numpy out:
+        H2D of the batch's ids + mask, `model.body_emb(ids.long(), mask.long())`, `IndexFlatIP.add`,
+        `model.query_emb`, `.cpu().numpy()`, `IndexFlatIP.search(numpy, k)` (N > 1: the driver's sharded search)."""
+        step_index.reset()
+        pi, pm = p_ids_h.to(dev, non_blocking=True), p_mask_h.to(dev, non_blocking=True)
+        qi, qm = q_ids_h.to(dev, non_blocking=True), q_mask_h.to(dev, non_blocking=True)
+        emb = model.body_emb(pi.long(), pm.long())
+        step_index.add(emb.reshape(pb * C, DIM))
+        q = model.query_emb(qi.long(), qm.long())
         if world > 1:
-            if rank == 0:
-                Ds = [torch.empty_like(D) for _ in range(world)]
-                Is = [torch.empty_like(I) for _ in range(world)]
-                dist.gather(D, Ds, dst=0)
-                dist.gather(I, Is, dst=0)
-                # the k-way merge of the per-shard lists is part of the job: it is inside the timed region of
-                # `value` as well as of `e2e`
-                _, Im = merge_topk_host([d.cpu().numpy() for d in Ds], [i.cpu().numpy() for i in Is], TOPK)
-                return Im
-            dist.gather(D, None, dst=0)
-            dist.gather(I, None, dst=0)
-            return None
-        if host:
-            D_h.copy_(D, non_blocking=True)
-            I_h.copy_(I, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return I_h
+            q_all = torch.empty((qb * world, DIM), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(q_all, q.contiguous())
+            return sharded_search(local_search, n_local, q_all, k)
+        _, I = index.search(q.cpu().numpy(), k)
         return I
 
     def sync():
@@ -291,24 +400,25 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(host: bool, steps: int):
+    def timed(fn, steps: int, wall: bool):
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
         for _ in range(steps):
-            step(host)
+            fn()
         e1.record()
         sync()
-        ms = e0.elapsed_time(e1) if not host else (time.time() - t0) * 1e3  # e2e includes host work: wall clock
+        ms = (time.time() - t0) * 1e3 if wall else e0.elapsed_time(e1)   # e2e includes host work: wall clock
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms / steps
 
-    for _ in range(max(3, args.warmup)):
-        step(False)
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        step_value()
     sync()
     launches0 = _lib.load().ance_launch_count()
     _lib.profile_enable(True)
@@ -316,81 +426,125 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms = timed(False, args.steps)
+    ms = timed(step_value, args.steps, wall=False)
     clocks = sampler.stop() if sampler else None
     prof = _lib.profile_read(reset=True)
     _lib.profile_enable(False)
     launches = _lib.load().ance_launch_count() - launches0
     st = index.stats()
-    step(True)
-    ms_e2e = timed(True, max(2, args.steps // 2))
+    step_e2e()
+    ms_e2e = timed(step_e2e, max(2, args.steps // 2), wall=True)
     # practical figure: MS-MARCO-like passage lengths ~ clipped N(76, 28), encoded with length
     # buckets (no FLOPs on all-padding tails).  Reported beside, never inside, `value`.
-    gl = torch.Generator().manual_seed(5)
-    mlens = torch.clamp(torch.normal(76.0, 28.0, (pb,), generator=gl).round(), 8, L_P).to(torch.int32).to(dev)
-    for _ in range(2):
-        model.encode_lens_bucketed(p_ids_d, mlens)
-    sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(2):
-        model.encode_lens_bucketed(p_ids_d, mlens)
-    e1.record()
-    sync()
-    ms_marco = e0.elapsed_time(e1) / 2
+    ms_marco = None
+    if wl["model"] == "rdot_nll":
+        gl = torch.Generator().manual_seed(5)
+        mlens = torch.clamp(torch.normal(76.0, 28.0, (pb,), generator=gl).round(), 8, L_p).to(torch.int32).to(dev)
+        for _ in range(2):
+            model.encode_lens_bucketed(p_ids_d, mlens)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            model.encode_lens_bucketed(p_ids_d, mlens)
+        e1.record()
+        sync()
+        ms_marco = e0.elapsed_time(e1) / 2
 
     if rank != 0:
         return
     units = (pb + qb) * world
     pk = peaks()
+    head = wl["head"]
     gemm_ms, gemm_n = prof["encoder_gemm"]
-    pruned = args.steps * (pb * PRUNED_FLOP_SEQ(L_P) + qb * PRUNED_FLOP_SEQ(L_Q))
-    gemm_flop = args.steps * (pb * GEMM_FLOP_SEQ(L_P) + qb * GEMM_FLOP_SEQ(L_Q)) - pruned  # executed
+    seqs_p = pb * C
+    pruned = args.steps * (seqs_p * pruned_flop_seq(Lc) + qb * pruned_flop_seq(L_q))
+    gemm_flop = args.steps * (seqs_p * gemm_flop_seq(Lc, head) + qb * gemm_flop_seq(L_q, head)) - pruned  # executed
     gemm_tf = gemm_flop / gemm_ms / 1e9
     coarse_ms, coarse_n = prof["coarse_search"]
     coarse_tf = args.steps * 2.0 * qb * world * n_local * DIM / coarse_ms / 1e9 if coarse_ms else None
     enc_ms = gemm_ms + prof["attention"][0] + prof["norm_embed"][0]
-    srch_ms = prof["quantize"][0] + coarse_ms + prof["rescore"][0] + prof["exact"][0]
+    srch_ms = coarse_ms + prof["rescore"][0] + prof["exact"][0]     # + the queries' share of `quantize` (negligible)
+    alg_flop = args.steps * (seqs_p * flop_seq(Lc, head) + qb * flop_seq(L_q, head))
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")
-    if os.path.exists(tp):
+    tp = os.path.join(ROOT, "profiles", "r02_ncu_gemm_traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")
+    if os.path.exists(tp) and wl is WORKLOADS["marco_psg"]:
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     out = {
-        "metric": METRIC, "value": units / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+        "metric": wl["metric"], "value": units / ms * 1e3, "unit": wl["unit"], "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.encoder_operand + " operands / fp32 accumulate",
+        "data": "synthetic", "config": workload_config(args, wl, world),
         "stages": {
-            "passages_encoded_per_s": (pb + qb * L_Q / L_P) * args.steps / enc_ms * 1e3 * world,
-            "queries_top200_per_s": qb * world * args.steps / srch_ms * 1e3,
+            "passages_encoded_per_s": (pb + qb * L_q / L_p) * args.steps / enc_ms * 1e3 * world,
+            "queries_topk_per_s": qb * world * args.steps / srch_ms * 1e3,
             "encode_ms_per_step": enc_ms / args.steps, "search_ms_per_step": srch_ms / args.steps,
-            "encode_frac_of_bf16_peak": ((args.steps * (pb * FLOP_SEQ(L_P) + qb * FLOP_SEQ(L_Q)) - pruned) / enc_ms / 1e9) / pk["bf16_tflops"],
-            "encode_flop_per_passage": {"algorithmic": FLOP_SEQ(L_P), "executed": FLOP_SEQ(L_P) - PRUNED_FLOP_SEQ(L_P)},
+            "index_add_ms_per_step": prof["quantize"][0] / args.steps,
+            "encode_frac_of_bf16_peak": ((alg_flop - pruned) / enc_ms / 1e9) / pk["bf16_tflops"],
+            "attention_share_of_encode": prof["attention"][0] / enc_ms,
+            "encode_flop_per_sequence": {"algorithmic": flop_seq(Lc, head), "executed": flop_seq(Lc, head) - pruned_flop_seq(Lc)},
             "search_coarse_tflops": coarse_tf,
             "search_coarse_frac_of_bf16_peak": coarse_tf / pk["bf16_tflops"] if coarse_tf else None,
             "search_stats": st,
-            "passages_per_s_marco_like_lengths": pb / ms_marco * 1e3 * world,
+            "passages_per_s_marco_like_lengths": (pb / ms_marco * 1e3 * world) if ms_marco else None,
         },
         "roofline": {"kernel": "tc05_gemm_kernel<EpStore> (encoder linear layers)", "bound": "tensor",
                      "achieved": gemm_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
-                     "traffic": traffic, "peak_source": pk["source"] + " of measured", "launches": gemm_n,
+                     "traffic": traffic, "peak_source": pk["source"], "launches": gemm_n,
                      "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                      "share_of_step": gemm_ms / (ms * args.steps)},
-        "e2e": {"value": units / ms_e2e * 1e3, "unit": UNIT,
-                "h2d_bytes_per_step": int(pb * (L_P * 4 + 4) + qb * (L_Q * 4 + 4)),
-                "d2h_bytes_per_step": int(qb * world * TOPK * 12)},
+        "e2e": {"value": units / ms_e2e * 1e3, "unit": wl["unit"],
+                "h2d_bytes_per_step": int(pb * L_p * 5 + qb * L_q * 5 + (0 if world > 1 else qb * DIM * 4)),
+                "d2h_bytes_per_step": int(qb * world * k * (8 if world > 1 else 12) + (0 if world > 1 else qb * DIM * 4)),
+                "path": "host ids+mask -> body_emb / query_emb (plugin calls) -> IndexFlatIP.add -> "
+                        + ("all-gather + sharded_search (driver)" if world > 1 else "IndexFlatIP.search(numpy)")},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+        "kernel_ms_per_step": {kk: v[0] / args.steps for kk, v in prof.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
-        threads = cpu_threads()
-        rate_p, rate_q, qps, dt = cpu_step_sample(threads, **CPU_BASELINE_SAMPLE)
+        base_sample, _ = cpu_samples(wl)
+        info = cpu_step_sample(wl, want_outputs=True, **base_sample)
+        o = info.pop("outputs")
         out["cpu_baseline"] = {
-            "value": cpu_value(pb, qb, rate_p, rate_q, qps), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": sample_text(CPU_BASELINE_SAMPLE) + "; %d threads (the reference pins faiss to 16, "
-                      "run_ann_data_gen.py:269); %.0f s of CPU work" % (threads, dt),
-            "passages_per_s": rate_p, "queries_top200_per_s": qps}
+            "value": cpu_value(pb, qb, info), "unit": wl["unit"], "cores": max(info["encode_threads"], info["search_threads"]),
+            "kind": "port", "sample": sample_text(wl, base_sample, info) + "; %.0f s of CPU work" % info["seconds"],
+            "passages_per_s": info["rate_p"], "queries_topk_per_s": info["qps_full"], "search_kind": info["search_kind"]}
+        # parity of the B200 path with the CPU arm on the very sample the CPU arm just computed (checker use of oracle/)
+        with torch.no_grad():
+            pi = o["p_ids"].to(dev)
+            if wl["model"] == "dpr":
+                pe, qe = model.body_emb(pi, pi != 0), model.query_emb(o["q_ids"].to(dev), o["q_ids"].to(dev) != 0)
+            elif C > 1:
+                pe = model.encode_lens_multi_chunk(pi, torch.full((pi.shape[0],), L_p, dtype=torch.int32, device=dev))
+                qe = model.encode_lens(o["q_ids"].to(dev), torch.full((o["q_ids"].shape[0],), L_q, dtype=torch.int32, device=dev))
+            else:
+                pe = model.encode_lens(pi, torch.full((pi.shape[0],), L_p, dtype=torch.int32, device=dev))
+                qe = model.encode_lens(o["q_ids"].to(dev), torch.full((o["q_ids"].shape[0],), L_q, dtype=torch.int32, device=dev))
+        pe, qe = pe.reshape(-1, DIM).cpu(), qe.cpu()
+        ref_p = o["p_emb"].reshape(-1, DIM)
+        small = IndexFlatIP(DIM, capacity=o["P"].shape[0], device=dev, operand=args.search_operand)
+        small.add(o["P"].to(dev))
+        Dg, Ig = small.search(o["Q"].numpy(), k)
+        same = float((torch.from_numpy(Ig) == o["I"]).all(dim=1).float().mean())
+        setov = float(np.mean([len(np.intersect1d(Ig[i], o["I"][i].numpy())) for i in range(Ig.shape[0])])) / k
+        out["parity"] = {
+            "encoder_min_cosine_vs_fp32_reference": float(torch.nn.functional.cosine_similarity(pe, ref_p, dim=-1).min()),
+            "encoder_max_abs_vs_fp32_reference": float(max((pe - ref_p).abs().max(), (qe - o["q_emb"]).abs().max())),
+            "search_topk_lists_identical_frac_vs_cpu_fp32": same, "search_topk_set_overlap_vs_cpu_fp32": setov,
+            "search_score_max_rel_diff": float(((torch.from_numpy(Dg) - o["D"]).abs().max() / o["D"].abs().max())),
+            "note": "CPU fp32 sgemm sums in a different order than the canonical fp64-accumulated score: lists may differ "
+                    "only where two scores are closer than fp32 summation noise; bit-exact parity vs the oracle is in tests/",
+            "overlap_at_200_vs_fp32_encoded_corpus": _load_overlap()}
     print(json.dumps(out))
+
+
+def _load_overlap():
+    """The 20,480-passage overlap@200 gate is a GPU test (tests/test_gpu_encoder.py); its last committed result."""
+    p = os.path.join(ROOT, "profiles", "r02_overlap_at_200.json")
+    return json.load(open(p)) if os.path.exists(p) else None
 
 
 def main():
@@ -399,15 +553,22 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--passages_per_step", type=int, default=37888)   # 64 encoder passes of 592 x 128 tokens
-    ap.add_argument("--queries_per_step", type=int, default=2368)     # 2 encoder passes of 1184 x 64 tokens (16:1)
-    ap.add_argument("--search_operand", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--workload", default="marco_psg", choices=sorted(WORKLOADS))
+    ap.add_argument("--passages_per_step", type=int, default=0, help="per GPU; 0 = the workload's default")
+    ap.add_argument("--queries_per_step", type=int, default=0, help="per GPU; 0 = the workload's default")
+    ap.add_argument("--search_operand", default="auto", choices=["auto", "fp16", "bf16"])
+    ap.add_argument("--encoder_operand", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    # defaults: marco_psg 64 encoder passes of 592 x 128 tokens + 2 of 1184 x 64 (16:1, the refresh's own 17.6:1);
+    # marco_doc_maxp 64 passes of 148 x 512 (2,368 documents) + 296 queries (8:1; real 8.75:1); dpr 64 passes of 296 x 256
+    args.passages_per_step = args.passages_per_step or wl["pb"]
+    args.queries_per_step = args.queries_per_step or wl["qb"]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_b200(args)
+        run_b200(args, wl)
 
 
 if __name__ == "__main__":
