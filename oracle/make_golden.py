@@ -407,6 +407,29 @@ def golden_dpr():
     print("dpr golden: hit@k", hits[0], hits[-1], "has_answer trues", sum(map(sum, table)))
 
 
+def golden_msmarco_mrr():
+    """MS MARCO MRR@10 from the reference's own utils/msmarco_eval.py:109-139 (pure Python, runs unmodified) on seeded
+    random rankings: pins ance_b200.evaluation.msmarco_mrr (notebook cell 8's `ms_mrr`)."""
+    from utils.msmarco_eval import compute_metrics
+    rng = np.random.default_rng(17)
+    cases = []
+    for n_q, n_judged, n_p in ((40, 50, 300), (7, 5, 30)):
+        relevant = {int(q): [int(x) for x in rng.choice(n_p, size=int(rng.integers(1, 4)), replace=False)]
+                    for q in rng.choice(1000, size=n_judged, replace=False)}
+        ranked = {}
+        qids = list(relevant)[:n_q // 2] + [int(q) for q in rng.integers(1000, 2000, size=n_q - n_q // 2)]
+        for q in qids:
+            lst = [int(x) for x in rng.permutation(n_p)[:int(rng.integers(3, 40))]]
+            if q in relevant and rng.random() < 0.7:   # plant a relevant passage somewhere in the first 15 ranks
+                lst[int(rng.integers(0, min(15, len(lst))))] = relevant[q][0]
+            ranked[q] = (lst + [0] * 1000)[:1000]
+        cases.append({"relevant": {str(k): v for k, v in relevant.items()}, "ranked": {str(k): v[:50] for k, v in ranked.items()},
+                      "mrr10": compute_metrics(relevant, ranked)["MRR @10"]})
+    with open(os.path.join(GOLD, "msmarco_mrr.json"), "w") as f:
+        json.dump(cases, f)
+    print("msmarco mrr golden:", [c["mrr10"] for c in cases])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     stub_third_party()
@@ -417,6 +440,7 @@ if __name__ == "__main__":
     golden_postprocess()
     golden_dpr()
     golden_trainer_records()
+    golden_msmarco_mrr()
     if "--no-encoders" not in sys.argv:
         golden_encoders()
         golden_trainer_losses()
