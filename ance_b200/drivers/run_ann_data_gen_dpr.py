@@ -31,6 +31,7 @@ import torch.distributed as dist
 
 from ..dpr_utils import AnswerMatcher, get_model_obj, load_mapping, load_states_from_checkpoint
 from ..models import MSMarcoConfigDict
+from .. import postprocess
 from . import run_ann_data_gen as base
 from .run_ann_data_gen import (B200Backend, all_gather_ids, all_gather_rows, get_checkpoint_no, get_latest_ann_data,
                                is_first_worker, sharded_search)

@@ -443,18 +443,31 @@ class BiEncoder(_B200Encoder):
         return ((-torch.log_softmax(logit_matrix, dim=1)[:, 0]).mean(),)
 
 
-class SEEDEncoderDot_NLL_LN(nn.Module):
-    """model/models.py:201-221 (`seeddot_nll`).  The SEED-Encoder backbone is a vendored fairseq-style model
-    outside the ANN-refresh scope of this package: the name resolves, construction
-    explains where to go."""
+def _reference_seed_class():
+    """The reference's own stock-PyTorch class, when the reference repository is importable (its directory on sys.path,
+    as its scripts arrange with `sys.path += ['../']`)."""
+    try:
+        from model.models import SEEDEncoderDot_NLL_LN as ref_cls   # /root/reference-style checkout
+        return ref_cls
+    except Exception as e:  # ImportError, or the reference's own third-party imports failing
+        raise NotImplementedError(
+            "seeddot_nll (SEED-Encoder, model/models.py:201-221) has no sm_100a kernels in ance_b200 — its backbone is a "
+            "vendored fairseq-style model outside the ANN-refresh scope (SURVEY.md par. 2.1 row 8) — and the reference's "
+            "stock module could not be imported to fall back to ({}: {}).  Put the reference checkout on sys.path to run "
+            "seeddot_nll through its own PyTorch code.".format(type(e).__name__, e)) from e
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError("seeddot_nll (SEED-Encoder) is not implemented by ance_b200; use the reference's "
-                                  "model/SEED_Encoder with its stock PyTorch modules")
+
+class SEEDEncoderDot_NLL_LN:
+    """model/models.py:201-221 (`seeddot_nll`).  The registry name resolves; construction / from_pretrained FALL BACK to
+    the reference's stock PyTorch module (SURVEY.md par. 2.1 row 8): the object returned is the reference's class, so
+    `query_emb` / `body_emb` behave exactly as upstream (no B200 acceleration)."""
+
+    def __new__(cls, *a, **k):
+        return _reference_seed_class()(*a, **k)
 
     @classmethod
     def from_pretrained(cls, *a, **k):
-        return cls()
+        return _reference_seed_class().from_pretrained(*a, **k)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -239,8 +239,34 @@ def test_registry_surface():
     for name in ("rdot_nll", "rdot_nll_multi_chunk", "dpr"):
         cls = MSMarcoConfigDict[name].model_class
         assert hasattr(cls, "query_emb") and hasattr(cls, "body_emb")
-    with pytest.raises(NotImplementedError):
-        MSMarcoConfigDict["seeddot_nll"].model_class()
+    # seeddot_nll resolves and FALLS BACK to the reference's stock module (SURVEY.md par. 2.1 row 8): without the
+    # reference checkout on sys.path that is a clear error, with it the reference's own class is what gets built
+    import sys
+    import types
+    saved = {k: sys.modules.pop(k) for k in ("model", "model.models") if k in sys.modules}
+    try:
+        with pytest.raises(NotImplementedError, match="stock module"):
+            MSMarcoConfigDict["seeddot_nll"].model_class()
+
+        class RefSeed:                       # stand-in for /root/reference/model/models.py:201-221
+            def __init__(self, config=None, model_argobj=None):
+                self.config = config
+
+            @classmethod
+            def from_pretrained(cls, path, **kw):
+                return cls(config=("loaded", path))
+
+        pkg, mod = types.ModuleType("model"), types.ModuleType("model.models")
+        mod.SEEDEncoderDot_NLL_LN = RefSeed
+        pkg.models = mod
+        sys.modules["model"], sys.modules["model.models"] = pkg, mod
+        m = MSMarcoConfigDict["seeddot_nll"].model_class("cfg")
+        assert type(m) is RefSeed and m.config == "cfg"
+        assert MSMarcoConfigDict["seeddot_nll"].model_class.from_pretrained("ckpt/").config == ("loaded", "ckpt/")
+    finally:
+        sys.modules.pop("model", None)
+        sys.modules.pop("model.models", None)
+        sys.modules.update(saved)
 
 
 def test_models_refuse_cpu_tensors():

@@ -72,13 +72,13 @@ def certify(N, nq, kinds):
             torch.cuda.empty_cache()
 
 
-def pace(N, nqs):
+def pace(N, nqs, windows=(0, 16, 32, 64, 128)):
     dev = torch.device("cuda:0")
     idx = build(N, "layernorm_clustered", "fp16", dev)
     Qall = queries(max(nqs), "layernorm_clustered", dev)
     for nq in nqs:
         Q = Qall[:nq].contiguous()
-        for window in (0, 16, 32, 64, 128):
+        for window in windows:
             idx.set_param("pace_window", window)
             ms, prof, st = timed_search(idx, Q, 200)
             c = prof["coarse_search"][0]
@@ -91,5 +91,7 @@ if __name__ == "__main__":
     _lib.profile_enable(True)
     if sys.argv[1] == "certify":
         certify(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4].split(","))
+    elif sys.argv[1] == "pace1":   # one configuration (the default window), short enough to sit under ncu
+        pace(int(sys.argv[2]), [int(x) for x in sys.argv[3].split(",")], windows=(32,))
     else:
         pace(int(sys.argv[2]), [int(x) for x in sys.argv[3].split(",")])
