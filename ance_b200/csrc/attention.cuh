@@ -41,6 +41,11 @@ struct Params {
   int hidden;          // heads * 64
   const float* kbias;  // [n_tokens] additive key bias * log2(e): 0 or -10000*log2e
   float scale_log2;    // log2(e) / sqrt(64)
+  // Variable-length packing (kPacked kernels only; null = uniform L): token row r of a 128-row tile belongs to a sequence
+  // that occupies the tile-local rows [row_lo[r], row_hi[r]) — whole sequences of ANY length <= 128 share a tile, nothing is
+  // padded inside a sequence (kbias is all zero), rows after the last sequence of a tile attend to themselves only.
+  const uint8_t* row_lo;
+  const uint8_t* row_hi;
 };
 
 struct Smem {
@@ -231,8 +236,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     for (int w = w_first; w < total_work; w += 2 * gridDim.x) {
       const int tile = w / p.heads, h = w - tile * p.heads;
       const int tok0 = tile * kTile;
-      const int seq_lo = (p.L >= kTile) ? 0 : (row / p.L) * p.L;   // keys of this row's own sequence
-      const int seq_hi = (p.L >= kTile) ? kTile : seq_lo + p.L;
+      const bool varlen = kPacked && p.row_lo != nullptr;
+      int seq_lo = (p.L >= kTile) ? 0 : (row / p.L) * p.L;   // keys of this row's own sequence
+      int seq_hi = (p.L >= kTile) ? kTile : seq_lo + p.L;
+      if (varlen) {
+        seq_lo = __ldg(p.row_lo + tok0 + row);
+        seq_hi = __ldg(p.row_hi + tok0 + row);
+      }
       float m_run = -INFINITY, l_run = 0.f;
       float o[kDh];
       if constexpr (!kSingle) {
@@ -256,7 +266,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const unsigned mk[4] = {smask[0], smask[1], smask[2], smask[3]};
         const bool plain = !kPacked && ((mk[0] | mk[1] | mk[2] | mk[3]) == 0u);
         int st[4];
-        {
+        if (varlen) {   // per row: chunk outside / inside / straddling the boundary of the row's own sequence
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            st[c] = (seq_hi <= c * 32 || seq_lo >= c * 32 + 32) ? 0 : (seq_lo <= c * 32 && seq_hi >= c * 32 + 32) ? 1 : 2;
+        } else {
           bool own[4], any_unmasked = false;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {

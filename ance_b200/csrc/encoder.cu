@@ -47,6 +47,8 @@ struct EmbedParams {
   uint16_t* X;           // [B*L, H] 16-bit (FMT)
   float* kbias;          // [B*L]  (1 - mask) * -10000 * log2e
   int* err_flag;
+  const int32_t* seq_row0;  // variable-length packing: first packed row of sequence b (null: row b*L); only the
+                            // len[b] real tokens are written, kbias is left alone (all zero)
 };
 
 template <int NV, uint32_t FMT>  // H = NV * 256
@@ -74,8 +76,11 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const EmbedParams p) {
     __syncthreads();
   }
   const int len = p.lens ? p.lens[b] : 0;
-  for (int t = warp; t < p.L; t += 8) {
-    const size_t tok = static_cast<size_t>(b) * p.L + t;
+  const bool varlen = p.seq_row0 != nullptr;
+  const size_t row0 = varlen ? static_cast<size_t>(p.seq_row0[b]) : static_cast<size_t>(b) * p.L;
+  const int t_end = varlen ? min(len, p.L) : p.L;
+  for (int t = warp; t < t_end; t += 8) {
+    const size_t tok = row0 + t;
     int id = ids[t];
     int ps = s_pos[t];
     if (id < 0 || id >= p.vocab || ps >= p.max_pos) {
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const EmbedParams p) {
                            (x[v * 8 + q * 2 + 1] - mean) * rstd * g[q * 2 + 1] + bb[q * 2 + 1]);
       out[v * 32 + lane] = make_uint4(h2[0], h2[1], h2[2], h2[3]);
     }
-    if (lane == 0) {
+    if (lane == 0 && !varlen) {
       const bool keep = p.mask ? (p.mask[tok] != 0) : (t < len);
       p.kbias[tok] = keep ? 0.f : -10000.0f * kLog2e;
     }
@@ -287,6 +292,16 @@ __global__ void gather_rows_f32_kernel(const uint16_t* __restrict__ X, size_t ro
     out[static_cast<size_t>(r) * H + c] = act16::Act<FMT>::to_float(X[static_cast<size_t>(r) * row_stride + c]);
 }
 
+// rows idx[r] of a 16-bit matrix [*, H] -> compact [n, H]  (variable-length packing: the CLS rows sit at arbitrary rows)
+__global__ void gather_rows16_by_index_kernel(const uint16_t* __restrict__ src, const int32_t* __restrict__ idx, int n, int H,
+                                              uint16_t* __restrict__ dst) {
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(idx[r]) * H);
+  uint4* o = reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) o[i] = __ldg(s + i);
+}
+
 template <uint32_t FMT>
 __global__ void act16_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -324,6 +339,9 @@ struct ance_encoder {
   // activations
   uint16_t *X = nullptr, *QKV = nullptr, *CTX = nullptr, *T = nullptr, *X1 = nullptr, *FF = nullptr;
   float* kbias = nullptr;
+  uint16_t *cls_ctx = nullptr, *cls_x = nullptr;   // [max_seqs, H]: CLS rows gathered for the pruned last layer (varlen)
+  int32_t* seq_row0 = nullptr;                     // [max_seqs] varlen plan: first packed row of each sequence
+  uint8_t *row_lo = nullptr, *row_hi = nullptr;    // [max_tokens] varlen plan: own-sequence key range of each packed row
   float* head_tmp = nullptr;  // [max_seqs, H] fp32
   int* err_flag = nullptr;
   uint16_t* dbg = nullptr;       // [(n_layer+1), max_tokens, H] when debugging
@@ -453,12 +471,19 @@ int set_attention_attrs() {
   return ANCE_OK;
 }
 
+// n_tiles > 0: variable-length packing — the plan (e->seq_row0 / row_lo / row_hi) is already on the device, the token
+// matrix has n_tiles * 128 rows and the CLS rows are gathered by index.
 template <uint32_t FMT>
 int forward_impl(ance_encoder* e, const int32_t* ids_dev, const int32_t* lens_dev, const uint8_t* mask_dev, int B, int L,
-                 float* out_dev, cudaStream_t st) {
+                 float* out_dev, cudaStream_t st, int n_tiles = 0) {
   const ance_encoder_config& c = e->cfg;
-  const int M = B * L, H = c.hidden, F = c.ffn;
+  const bool varlen = n_tiles > 0;
+  const int M = varlen ? n_tiles * attn::kTile : B * L, H = c.hidden, F = c.ffn;
   int rc;
+  if (varlen) {   // rows behind the last sequence of a tile: zeros (finite through every layer), no key bias anywhere
+    ANCE_CUDA(cudaMemsetAsync(e->X, 0, static_cast<size_t>(M) * H * 2, st));
+    ANCE_CUDA(cudaMemsetAsync(e->kbias, 0, static_cast<size_t>(M) * 4, st));
+  }
   // K1
   EmbedParams ep;
   ep.ids = ids_dev; ep.lens = lens_dev; ep.mask = mask_dev;
@@ -468,6 +493,7 @@ int forward_impl(ance_encoder* e, const int32_t* ids_dev, const int32_t* lens_de
   ep.word = e->word; ep.pos = e->pos; ep.type = e->type;
   ep.gamma = e->eg; ep.beta = e->eb; ep.eps = c.ln_eps;
   ep.X = e->X; ep.kbias = e->kbias; ep.err_flag = e->err_flag;
+  ep.seq_row0 = varlen ? e->seq_row0 : nullptr;
   ance::prof_begin(ance::kClsNorm, st);
   switch (H / 256) {
     case 1: embed_ln_kernel<1, FMT><<<B, 256, 0, st>>>(ep); break;
@@ -491,16 +517,18 @@ int forward_impl(ance_encoder* e, const int32_t* ids_dev, const int32_t* lens_de
     return ANCE_ERR_CUDA;
   }
   attn::Params ap;
-  ap.n_tokens = M; ap.L = L; ap.heads = c.heads; ap.hidden = H;
+  ap.n_tokens = M; ap.L = varlen ? 64 : L; ap.heads = c.heads; ap.hidden = H;   // varlen: any L < 128 selects the packed kernel
   ap.kbias = e->kbias;
   ap.scale_log2 = kLog2e / 8.0f;
+  ap.row_lo = varlen ? e->row_lo : nullptr;
+  ap.row_hi = varlen ? e->row_hi : nullptr;
   const int attn_work = ((M + 127) / 128) * c.heads;
   const int attn_grid = std::min(attn_work, gemm::sm_count());
   for (int l = 0; l < c.n_layer; ++l) {
     const LayerDev& d = e->layers[l];
     if ((rc = linear<FMT>(e->X, H, M, d.wqkv, 3 * H, H, d.bqkv, nullptr, 0, e->QKV, nullptr, st, ance::kClsGemmQkv))) return rc;
     ance::prof_begin(ance::kClsAttn, st);
-    if (L < attn::kTile) attn::attention_kernel<true, true, FMT><<<attn_grid, attn::kThreads, attn::Smem::kDynamic, st>>>(tmQKV, tmCTX, ap);
+    if (varlen || L < attn::kTile) attn::attention_kernel<true, true, FMT><<<attn_grid, attn::kThreads, attn::Smem::kDynamic, st>>>(tmQKV, tmCTX, ap);
     else if (L == attn::kTile) attn::attention_kernel<false, true, FMT><<<attn_grid, attn::kThreads, attn::Smem::kDynamic, st>>>(tmQKV, tmCTX, ap);
     else attn::attention_kernel<false, false, FMT><<<attn_grid, attn::kThreads, attn::Smem::kDynamic, st>>>(tmQKV, tmCTX, ap);
     ance::prof_end(ance::kClsAttn, st);
@@ -508,10 +536,19 @@ int forward_impl(ance_encoder* e, const int32_t* ids_dev, const int32_t* lens_de
     ance::count_launch(1);
     // In the last layer only token 0 of every sequence is read downstream (models.py:49,193): run the
     // out-projection, FFN and both LayerNorms on those B rows only (strided TMA views, compact outputs).
-    const bool cls_only = e->prune_last_layer && (l == c.n_layer - 1);
+    const bool cls_only = (e->prune_last_layer || varlen) && (l == c.n_layer - 1);
     const int Mr = cls_only ? B : M;                                    // rows processed from here on
-    const size_t pitch = cls_only ? static_cast<size_t>(L) * H : H;     // row pitch of CTX / X views
-    if ((rc = linear<FMT>(e->CTX, pitch, Mr, d.wo, H, H, d.bo, e->X, 0, e->T, nullptr, st, ance::kClsGemmOut, pitch))) return rc;
+    const uint16_t *ctx_a = e->CTX, *res_x = e->X;
+    size_t pitch = cls_only ? static_cast<size_t>(L) * H : H;           // row pitch of CTX / X views
+    if (cls_only && varlen) {   // the CLS rows sit at seq_row0[b]: gather them into compact [B, H] operands
+      ance::ProfScope ps(ance::kClsNorm, st);
+      gather_rows16_by_index_kernel<<<B, 96, 0, st>>>(e->CTX, e->seq_row0, B, H, e->cls_ctx);
+      gather_rows16_by_index_kernel<<<B, 96, 0, st>>>(e->X, e->seq_row0, B, H, e->cls_x);
+      ANCE_CUDA(cudaGetLastError());
+      ance::count_launch(2);
+      ctx_a = e->cls_ctx; res_x = e->cls_x; pitch = H;
+    }
+    if ((rc = linear<FMT>(ctx_a, pitch, Mr, d.wo, H, H, d.bo, res_x, 0, e->T, nullptr, st, ance::kClsGemmOut, pitch))) return rc;
     if ((rc = layer_norm<FMT>(e->T, false, H, Mr, H, d.ln1g, d.ln1b, c.ln_eps, e->X1, nullptr, st))) return rc;
     if ((rc = linear<FMT>(e->X1, H, Mr, d.w1, F, H, d.b1, nullptr, 1, e->FF, nullptr, st, ance::kClsGemmFfn1))) return rc;
     if ((rc = linear<FMT>(e->FF, F, Mr, d.w2, H, F, d.b2, e->X1, 0, e->T, nullptr, st, ance::kClsGemmFfn2))) return rc;
@@ -519,7 +556,7 @@ int forward_impl(ance_encoder* e, const int32_t* ids_dev, const int32_t* lens_de
     if (e->dbg && M <= e->dbg_tokens)  // with cls_only the first B rows hold the CLS rows of the last layer
       ANCE_CUDA(cudaMemcpyAsync(e->dbg + static_cast<size_t>(l + 1) * e->dbg_tokens * H, e->X, static_cast<size_t>(Mr) * H * 2, cudaMemcpyDeviceToDevice, st));
   }
-  const size_t cls_pitch = e->prune_last_layer ? static_cast<size_t>(H) : static_cast<size_t>(L) * H;
+  const size_t cls_pitch = (e->prune_last_layer || varlen) ? static_cast<size_t>(H) : static_cast<size_t>(L) * H;
   // K7: CLS rows (token 0 of every sequence) -> head
   if (c.has_head) {
     // A = the CLS rows of X ([B, H] compact after the pruned last layer, else row pitch L*H)
@@ -613,6 +650,11 @@ extern "C" int ance_encoder_create(const ance_encoder_config* cfg, const ance_en
   chk(e->X1 = dev_alloc<uint16_t>(e, T * H));
   chk(e->FF = dev_alloc<uint16_t>(e, T * F));
   chk(e->kbias = dev_alloc<float>(e, T));
+  chk(e->cls_ctx = dev_alloc<uint16_t>(e, T / 16 * H));
+  chk(e->cls_x = dev_alloc<uint16_t>(e, T / 16 * H));
+  chk(e->seq_row0 = dev_alloc<int32_t>(e, T / 16));
+  chk(e->row_lo = dev_alloc<uint8_t>(e, T));
+  chk(e->row_hi = dev_alloc<uint8_t>(e, T));
   chk(e->head_tmp = dev_alloc<float>(e, T / 16 * H));
   chk(e->err_flag = dev_alloc<int>(e, 1));
   if (!ok || cudaGetLastError() != cudaSuccess) {
@@ -655,6 +697,108 @@ extern "C" int ance_encoder_forward(ance_encoder_t e, const int32_t* ids_dev, co
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (e->fmt == tc05::kFmtBF16) return forward_impl<tc05::kFmtBF16>(e, ids_dev, lens_dev, mask_dev, B, L, out_dev, st);
   return forward_impl<tc05::kFmtF16>(e, ids_dev, lens_dev, mask_dev, B, L, out_dev, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// variable-length forward: whole sequences of any length <= 128 packed into 128-row attention tiles
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// Online best-fit of sequences first .. (in order) into at most cap_tiles tiles of 128 rows: every sequence goes to the
+// fullest tile that still has room for it (all tiles of the chunk stay open, so this packs almost as well as an offline
+// pass).  Stops at the first sequence that fits nowhere, or at max_seqs.  Returns the number of sequences placed.
+int pack_chunk(const int32_t* lens, int first, int B, int cap_tiles, int max_seqs, std::vector<int32_t>& row0,
+               std::vector<uint8_t>& lo, std::vector<uint8_t>& hi, int* n_tiles_out) {
+  constexpr int T = attn::kTile;
+  std::vector<int> used;            // rows used per tile
+  std::vector<int> head(T + 1, -1); // head[f] = a tile with exactly f free rows (intrusive lists through next[])
+  std::vector<int> next;
+  row0.clear();
+  auto push = [&](int tile) { const int f = T - used[tile]; next[tile] = head[f]; head[f] = tile; };
+  int placed = 0;
+  for (int b = first; b < B && placed < max_seqs; ++b) {
+    const int len = lens[b];
+    int tile = -1;
+    for (int f = len; f <= T; ++f)   // smallest free space that fits = fullest tile
+      if (head[f] >= 0) { tile = head[f]; head[f] = next[tile]; break; }
+    if (tile < 0) {
+      if (static_cast<int>(used.size()) >= cap_tiles) break;
+      tile = static_cast<int>(used.size());
+      used.push_back(0);
+      next.push_back(-1);
+    }
+    row0.push_back(tile * T + used[tile]);
+    used[tile] += len;
+    if (used[tile] < T) push(tile);
+    ++placed;
+  }
+  const int n_tiles = static_cast<int>(used.size());
+  lo.assign(static_cast<size_t>(n_tiles) * T, 0);
+  hi.assign(static_cast<size_t>(n_tiles) * T, 0);
+  for (int r = 0; r < n_tiles * T; ++r) {   // default: a row behind the last sequence of its tile attends to itself
+    lo[r] = static_cast<uint8_t>(r % T);
+    hi[r] = static_cast<uint8_t>(r % T + 1);
+  }
+  for (int i = 0; i < placed; ++i) {
+    const int r0 = row0[i], len = lens[first + i];
+    for (int t = 0; t < len; ++t) {
+      lo[r0 + t] = static_cast<uint8_t>(r0 % T);
+      hi[r0 + t] = static_cast<uint8_t>(r0 % T + len);
+    }
+  }
+  *n_tiles_out = n_tiles;
+  return placed;
+}
+
+}  // namespace
+
+// host-only view of the tile packing (tests): plans the FIRST chunk of lens[0..B) for a handle of `max_tokens`
+extern "C" int ance_dbg_pack_varlen(const int32_t* lens_host, int B, int max_tokens, int32_t* row0_out, uint8_t* lo_out,
+                                    uint8_t* hi_out, int* n_placed, int* n_tiles) {
+  ANCE_REQUIRE(lens_host && row0_out && n_placed && n_tiles && B > 0 && max_tokens >= attn::kTile, "ance_dbg_pack_varlen: bad arguments");
+  for (int b = 0; b < B; ++b) ANCE_REQUIRE(lens_host[b] >= 1 && lens_host[b] <= attn::kTile, "ance_dbg_pack_varlen: length %d out of range", lens_host[b]);
+  std::vector<int32_t> row0;
+  std::vector<uint8_t> lo, hi;
+  *n_placed = pack_chunk(lens_host, 0, B, max_tokens / attn::kTile, max_tokens / 16, row0, lo, hi, n_tiles);
+  memcpy(row0_out, row0.data(), row0.size() * 4);
+  if (lo_out) memcpy(lo_out, lo.data(), lo.size());
+  if (hi_out) memcpy(hi_out, hi.data(), hi.size());
+  return ANCE_OK;
+}
+
+extern "C" int ance_encoder_forward_varlen(ance_encoder_t e, const int32_t* ids_dev, const int32_t* lens_dev,
+                                           const int32_t* lens_host, int B, int L, float* out_dev, void* stream) {
+  ANCE_REQUIRE(e != nullptr, "ance_encoder_forward_varlen: null handle");
+  ANCE_REQUIRE(ids_dev && lens_dev && lens_host && out_dev, "ance_encoder_forward_varlen: null buffer");
+  ANCE_REQUIRE(B > 0 && L > 0 && L <= attn::kTile, "ance_encoder_forward_varlen: need B > 0 and 0 < L <= 128 (got B = %d, L = %d); "
+               "longer sequences go through ance_encoder_forward", B, L);
+  const ance_encoder_config& c = e->cfg;
+  ANCE_REQUIRE(L + (c.arch == ANCE_ARCH_ROBERTA ? c.pad_id + 1 : 0) <= c.max_pos, "ance_encoder_forward_varlen: L = %d exceeds max_position_embeddings %d", L, c.max_pos);
+  for (int b = 0; b < B; ++b)
+    ANCE_REQUIRE(lens_host[b] >= 1 && lens_host[b] <= L, "ance_encoder_forward_varlen: length %d of sequence %d outside [1, %d]", lens_host[b], b, L);
+  int dev = -1;
+  ANCE_CUDA(cudaGetDevice(&dev));
+  ANCE_REQUIRE(dev == e->device, "ance_encoder_forward_varlen: the handle belongs to device %d but device %d is current", e->device, dev);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int cap_tiles = e->max_tokens / attn::kTile, max_seqs = e->max_tokens / 16;
+  std::vector<int32_t> row0;
+  std::vector<uint8_t> lo, hi;
+  for (int first = 0; first < B;) {
+    int n_tiles = 0;
+    const int n = pack_chunk(lens_host, first, B, cap_tiles, max_seqs, row0, lo, hi, &n_tiles);
+    // the plan arrays are read by the kernels of this chunk only; pageable cudaMemcpyAsync stages them before returning
+    ANCE_CUDA(cudaMemcpyAsync(e->seq_row0, row0.data(), static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
+    ANCE_CUDA(cudaMemcpyAsync(e->row_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice, st));
+    ANCE_CUDA(cudaMemcpyAsync(e->row_hi, hi.data(), hi.size(), cudaMemcpyHostToDevice, st));
+    const int32_t* ids = ids_dev + static_cast<size_t>(first) * L;
+    float* out = out_dev + static_cast<size_t>(first) * c.hidden;
+    const int rc = (e->fmt == tc05::kFmtBF16)
+                       ? forward_impl<tc05::kFmtBF16>(e, ids, lens_dev + first, nullptr, n, L, out, st, n_tiles)
+                       : forward_impl<tc05::kFmtF16>(e, ids, lens_dev + first, nullptr, n, L, out, st, n_tiles);
+    if (rc) return rc;
+    first += n;
+  }
+  return ANCE_OK;
 }
 
 extern "C" int ance_encoder_set_param(ance_encoder_t e, const char* name, double value) {

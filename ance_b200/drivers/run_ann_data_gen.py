@@ -166,6 +166,7 @@ class B200Backend:
         B = args.per_gpu_eval_batch_size
         per = max(B, (args.encode_batch_tokens // L) // B * B)  # super-batch, a multiple of the reference batch
         bucketed = self.mask_mode != "nonzero" and not multi and getattr(args, "length_buckets", True)
+        varlen = bucketed and L <= 128 and getattr(args, "varlen", True) and hasattr(self.model, "encode_lens_varlen")
         if bucketed:
             per *= 8   # every length bucket of a super-batch should still fill the GPU (the encoder re-splits by tokens)
         reader = StridedBatchReader(cache, per, rank=rank, world_size=W)
@@ -192,6 +193,9 @@ class B200Backend:
                     e = self.model.encode_lens_multi_chunk(ids_d, lens_d)
                     e, i = rows_from_batches(e, idx.numpy(), B)
                     out.copy_(e)
+                elif varlen:
+                    self.model.encode_lens_varlen(ids_d, lens_d, lens_host=lens, out=out)
+                    i = idx.numpy()
                 elif bucketed:
                     self.model.encode_lens_bucketed(ids_d, lens_d, out=out)
                     i = idx.numpy()
@@ -501,6 +505,9 @@ def get_arguments(argv=None):
                    help="draw the negative-sampling order from Python's `random` exactly as the reference does")
     p.add_argument("--seed", default=None, type=int, help="seed for the sampling order (reference: unseeded)")
     p.add_argument("--poll_seconds", default=60, type=int)
+    p.add_argument("--no_varlen", dest="varlen", action="store_false",
+                   help="L <= 128 caches: group sequences into padded length buckets instead of packing whole sequences of any "
+                        "length into 128-token attention tiles (same embeddings up to fp32 summation order)")
     p.add_argument("--no_length_buckets", dest="length_buckets", action="store_false",
                    help="encode every sequence at the cache's full padded length (the reference's behaviour); by default "
                         "sequences are grouped by the smallest supported padded length, which yields the same embeddings")

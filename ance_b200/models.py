@@ -182,6 +182,29 @@ class _CudaEncoder:
         return out
 
 
+def _forward_varlen(self, ids: torch.Tensor, lens: torch.Tensor, lens_host: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ids int32 [B, L <= 128] CUDA, lens int32 [B] CUDA (+ the same lengths on the host, else they are copied back):
+    only the real tokens are computed (ance_encoder_forward_varlen).  -> fp32 [B, H]."""
+    B, L = ids.shape
+    if out is None:
+        out = torch.empty((B, self.hidden_size), dtype=torch.float32, device=ids.device)
+    elif out.shape != (B, self.hidden_size) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != ids.device:
+        raise ValueError("out must be a contiguous float32 tensor [B, hidden] on the inputs' device")
+    if lens_host is None:
+        lens_host = lens.cpu()
+    lens_host = lens_host.to(torch.int32).contiguous()
+    if lens_host.device.type != "cpu" or lens_host.shape != (B,):
+        raise ValueError("lens_host must be a CPU tensor [B]")
+    with torch.cuda.device(ids.device):
+        _lib.check(self.lib.ance_encoder_forward_varlen(self.h, ids.data_ptr(), lens.data_ptr(), lens_host.data_ptr(), B, L,
+                                                        out.data_ptr(), _lib.current_stream()))
+    return out
+
+
+_CudaEncoder.forward_varlen = _forward_varlen
+
+
 class _B200Encoder(nn.Module):
     """Common machinery: lazily (re)build the CUDA encoder when the parameters move or change."""
 
@@ -322,6 +345,13 @@ class RobertaDot_NLL_LN(_B200Encoder):
     # fast path used by the B200 refresher: mask given as lengths (msmarco_data.py:282 form)
     def encode_lens(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         return self._encoder(ids_i32.device).forward(ids_i32.contiguous(), lens_i32.contiguous(), None, out=out)
+
+    def encode_lens_varlen(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor, lens_host: Optional[torch.Tensor] = None,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Same result as encode_lens (up to fp32 summation order inside a tile's softmax) at the cost of the REAL tokens
+        only: whole sequences of any length are packed into 128-token attention tiles.  L <= 128 (the MS MARCO passage and
+        query caches); longer caches use encode_lens_bucketed."""
+        return self._encoder(ids_i32.device).forward_varlen(ids_i32.contiguous(), lens_i32.contiguous(), lens_host, out=out)
 
     def encode_lens_bucketed(self, ids_i32: torch.Tensor, lens_i32: torch.Tensor, min_bucket: int = 16,
                              out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -139,6 +139,15 @@ int ance_encoder_destroy(ance_encoder_t enc);
  * finite "uniform attention" vector the reference yields.  out_dev [B, hidden] fp32. */
 int ance_encoder_forward(ance_encoder_t enc, const int32_t* ids_dev, const int32_t* lens_dev,
                          const uint8_t* mask_dev, int B, int L, float* out_dev, void* stream);
+/* Variable-length form of the same forward for L <= 128 (the MS MARCO passage / query caches): sequence b has lens[b]
+ * real tokens followed by padding (data/msmarco_data.py:275-303), and only the real tokens are computed.  Whole sequences
+ * are packed into 128-row attention tiles (a tile holds sequences of ANY lengths, none straddles a tile, every sequence
+ * attends to its own tokens only), the linear layers and LayerNorms run on the packed token matrix, the CLS rows are
+ * gathered for the last layer and the head.  lens_dev and lens_host hold the same B lengths, each in [1, L] (the tile
+ * packing is planned on the host); B is unlimited (the call splits by the handle's max_tokens).  Embeddings equal those of
+ * ance_encoder_forward up to fp32 summation order inside the softmax / P*V of a tile (tests: |diff| <= 2e-3). */
+int ance_encoder_forward_varlen(ance_encoder_t enc, const int32_t* ids_dev, const int32_t* lens_dev,
+                                const int32_t* lens_host, int B, int L, float* out_dev, void* stream);
 /* Tunables: "prune_last_layer" (default 1): in the last layer only token 0 of every sequence is read
  * downstream, so out-projection / FFN / LayerNorm run on those rows only (result-identical; bench.py reports
  * the executed FLOPs beside the algorithmic ones).  "ln_rows_per_warp" (1, 2 or 4; default 2, process-wide): rows a warp
@@ -171,6 +180,11 @@ int ance_profile_read(double* ms_by_class, int64_t* launches_by_class, int n, in
  * ------------------------------------------------------------------------------------------------ */
 /* D[M,N] = act(A[M,K] * B[N,K]^T + bias) + R ; A,B 16-bit device arrays in `fmt`; outputs optional.
  * variant: 0 = BN 256 CG 1, 1 = BN 128 CG 1, 2 = BN 256 CG 2, 3 = BN 128 CG 2, 4 = BN 64 CG 1 */
+/* Host-only: the tile plan ance_encoder_forward_varlen makes for the first chunk of lens_host[0..B) on a handle created with
+ * `max_tokens`: row0_out[i] = packed row of sequence i's first token (i < *n_placed), lo/hi_out [*n_tiles * 128] = own-sequence
+ * key range of every packed row (may be null). */
+int ance_dbg_pack_varlen(const int32_t* lens_host, int B, int max_tokens, int32_t* row0_out, uint8_t* lo_out,
+                         uint8_t* hi_out, int* n_placed, int* n_tiles);
 int ance_dbg_gemm(const void* A_dev, const void* B_dev, int M, int N, int K, int fmt, int variant,
                   const float* bias_dev, const void* residual_bf16_dev, int act, void* C_bf16_dev,
                   float* C_f32_dev, void* stream);

@@ -280,3 +280,39 @@ def test_retrieval_overlap_at_200(rdot):
     assert report["fp16"]["max_abs"] <= MAXABS, report
     assert report["fp16"]["overlap_at_200"] >= 0.99, report
     assert report["bf16"]["max_abs"] <= MAXABS_BF16, report
+
+
+def test_varlen_packing_matches_dense():
+    """ance_encoder_forward_varlen (whole sequences of any length packed into 128-token attention tiles, only real tokens
+    computed) against the dense padded forward of the same sequences.  Not bit-identical by construction: a sequence sits at
+    a different offset of its tile, which changes the grouping of the softmax row sum and the order of the P*V
+    accumulation (fp32) — same bound as the bucketed path."""
+    from ance_b200.models import RobertaDot_NLL_LN
+    m = RobertaDot_NLL_LN(_cfg())
+    m.load_state_dict(random_roberta_state_dict(seed=0), strict=True)
+    m.max_tokens = 4096            # small handle: 900 sequences need several chunks of <= 32 tiles
+    m = m.cuda().eval()
+    rng = np.random.default_rng(21)
+    lens = np.clip(rng.normal(76, 28, size=900).round(), 1, 128).astype(np.int32)
+    lens[:6] = [1, 128, 127, 2, 64, 65]
+    ids = rng.integers(3, 50265, size=(900, 128)).astype(np.int32)
+    ids[np.arange(128)[None, :] >= lens[:, None]] = 1
+    ids[:, 0] = 0
+    ids_d, lens_d = torch.from_numpy(ids).cuda(), torch.from_numpy(lens).cuda()
+    dense = m.encode_lens(ids_d, lens_d)
+    var = m.encode_lens_varlen(ids_d, lens_d, lens_host=torch.from_numpy(lens))
+    var2 = m.encode_lens_varlen(ids_d, lens_d)                       # host lengths fetched from the device copy
+    m.check_inputs()
+    assert torch.isfinite(var).all() and torch.equal(var, var2)
+    assert torch.allclose(dense, var, rtol=0, atol=2e-3), (dense - var).abs().max().item()
+    assert torch.nn.functional.cosine_similarity(dense, var, dim=-1).min().item() > 0.999999
+    # a sequence's embedding does not depend on what it shares a tile with
+    one = m.encode_lens_varlen(ids_d[7:8].contiguous(), lens_d[7:8].contiguous())
+    assert torch.allclose(one[0], var[7], rtol=0, atol=2e-3)
+    # queries: L = 64
+    q = m.encode_lens_varlen(ids_d[:300, :64].contiguous(), lens_d[:300].clamp(max=64))
+    qd = m.encode_lens(ids_d[:300, :64].contiguous(), lens_d[:300].clamp(max=64))
+    assert torch.allclose(q, qd, rtol=0, atol=2e-3)
+    from ance_b200._lib import AnceError
+    with pytest.raises(AnceError):                                   # L > 128 is the padded / bucketed path's business
+        m.encode_lens_varlen(torch.zeros(2, 256, dtype=torch.int32, device="cuda"), torch.ones(2, dtype=torch.int32, device="cuda"))
