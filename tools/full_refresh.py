@@ -47,7 +47,7 @@ def main():
     ap.add_argument("--n_dev", type=int, default=6980)
     ap.add_argument("--lengths", default="full", choices=["full", "marco"],
                     help="full: every passage has 128 real tokens (the roofline regime, SURVEY.md 8d); marco: clipped N(76, 28)")
-    ap.add_argument("--work_dir", default="/dev/shm/ance_full_refresh")
+    ap.add_argument("--work_dir", default="", help="default: /dev/shm/ance_full_refresh when it has room, else /tmp/ance_full_refresh")
     ap.add_argument("--topk_training", type=int, default=200)
     ap.add_argument("--negative_sample", type=int, default=20)
     ap.add_argument("--n_layer", type=int, default=12)
@@ -66,6 +66,13 @@ def main():
         dist.init_process_group("nccl")
     barrier = (lambda: dist.barrier()) if W > 1 else (lambda: None)
 
+    if not a.work_dir:
+        need = a.n_passages * 516 + (a.n_queries + a.n_dev) * 260 + (2 << 30)
+        try:
+            shm_ok = shutil.disk_usage("/dev/shm").free > need
+        except OSError:
+            shm_ok = False
+        a.work_dir = "/dev/shm/ance_full_refresh" if shm_ok else "/tmp/ance_full_refresh"
     data, ckpt, out = (os.path.join(a.work_dir, x) for x in ("data", "init_model", "ann"))
     t0 = time.time()
     if rank == 0:
