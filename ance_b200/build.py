@@ -49,9 +49,22 @@ def _stale(target: Path, deps) -> bool:
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
-    srcs, hdrs = _sources(), _headers()
+    """Serialised across processes by an flock on build/.lock: when the .so is missing every rank of a torchrun job
+    lands here at once, and they must not write the same object / .so.tmp files concurrently.  The first one builds,
+    the others find the library up to date when they get the lock."""
+    import fcntl
     LIBDIR.mkdir(parents=True, exist_ok=True)
     OBJDIR.mkdir(parents=True, exist_ok=True)
+    with open(OBJDIR.parent / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_cuda_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_cuda_locked(force: bool, verbose: bool) -> Path:
+    srcs, hdrs = _sources(), _headers()
     if not force and not _stale(LIB, srcs + hdrs + [Path(__file__)]):
         return LIB
     nvcc = _nvcc()

@@ -647,7 +647,7 @@ struct ance_index {
   uint16_t* P16 = nullptr;   // [cap, dim]
   unsigned int* pstats = nullptr;  // [2]
   // tunables
-  int kprime = 0, n_splits = 0, cta_group = 2, max_ctas = 0, exact_fallback = 1, tier2 = 1, pace_window = 32;
+  int kprime = 0, n_splits = 0, cta_group = 2, max_ctas = 0, exact_fallback = 1, tier2 = 1, pace_window = 16;
   // workspace (grown lazily)
   uint16_t* Q16 = nullptr; float* qn_hat = nullptr; float* qn_delta = nullptr; int64_t q_cap = 0;
   float* scratch_sc = nullptr; int* scratch_id = nullptr; size_t scratch_elems = 0;

@@ -92,6 +92,6 @@ if __name__ == "__main__":
     if sys.argv[1] == "certify":
         certify(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4].split(","))
     elif sys.argv[1] == "pace1":   # one configuration (the default window), short enough to sit under ncu
-        pace(int(sys.argv[2]), [int(x) for x in sys.argv[3].split(",")], windows=(32,))
+        pace(int(sys.argv[2]), [int(x) for x in sys.argv[3].split(",")], windows=(16,))
     else:
         pace(int(sys.argv[2]), [int(x) for x in sys.argv[3].split(",")])

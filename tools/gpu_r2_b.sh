@@ -10,7 +10,7 @@ timeout 900 python tools/exp_search_r2.py pace 8841823 18944,75776 > gpurun_out/
 timeout 1500 python tools/exp_search_r2.py certify 8841823 18944 layernorm_clustered,iid,heavy_tail,near_duplicate,dpr > gpurun_out/b_certify.log 2>&1
 tail -20 gpurun_out/b_certify.log | cut -c1-420
 # ncu: coarse search in the tensor regime with the soft barrier (dram bytes), first two coarse launches after warm-up
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:EpTopK -s 1 -c 2 -o gpurun_out/prof_r2_search \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc05_gemm_kernel -s 1 -c 2 -o gpurun_out/prof_r2_search \
   python tools/exp_search_r2.py pace1 8841823 18944 > gpurun_out/b_ncu_search.log 2>&1
 echo "ncu search rc=$?"
 timeout 600 python bench.py --workload marco_doc_maxp --steps 3 --warmup 3 > gpurun_out/b_bench_maxp.json 2> gpurun_out/b_bench_maxp.err
