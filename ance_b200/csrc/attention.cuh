@@ -264,7 +264,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         // masked while the row has an unmasked key somewhere: exp2(-10000 log2e + s - m) flushes to zero, as
         // exp(-10000 + s - m) does in the reference's fp32 softmax),  1 = no key masked (no bias term),  2 = general.
         const unsigned mk[4] = {smask[0], smask[1], smask[2], smask[3]};
-        const bool plain = !kPacked && ((mk[0] | mk[1] | mk[2] | mk[3]) == 0u);
+        // (variable-length tiles: a row whose sequence fills the whole tile takes the same arithmetic as a full-length
+        // sequence of the dense L = 128 kernel, so that the two paths agree bit for bit)
+        const bool plain = kPacked ? (varlen && seq_lo == 0 && seq_hi == kTile) : ((mk[0] | mk[1] | mk[2] | mk[3]) == 0u);
         int st[4];
         if (varlen) {   // per row: chunk outside / inside / straddling the boundary of the row's own sequence
 #pragma unroll

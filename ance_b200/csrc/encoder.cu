@@ -347,6 +347,7 @@ struct ance_encoder {
   uint16_t* dbg = nullptr;       // [(n_layer+1), max_tokens, H] when debugging
   int dbg_tokens = 0;
   int prune_last_layer = 1;  // last layer: only the CLS rows go through out-proj / FFN (identical result)
+  int varlen_align = 1;      // ance_encoder_forward_varlen: slot alignment inside a tile (1 | 16), see pack_chunk
   std::vector<void*> allocs;
 };
 
@@ -707,7 +708,11 @@ namespace {
 // Online best-fit of sequences first .. (in order) into at most cap_tiles tiles of 128 rows: every sequence goes to the
 // fullest tile that still has room for it (all tiles of the chunk stay open, so this packs almost as well as an offline
 // pass).  Stops at the first sequence that fits nowhere, or at max_seqs.  Returns the number of sequences placed.
-int pack_chunk(const int32_t* lens, int first, int B, int cap_tiles, int max_seqs, std::vector<int32_t>& row0,
+// align: every sequence starts at a multiple of `align` rows of its tile (its slot is padded up to a multiple).  With
+// align = 16 — the K step of a 16-bit tcgen05.mma — the P*V accumulation and the softmax row sum of a sequence group their
+// terms exactly as they do at offset 0, so its embedding does not depend on what else is in the tile and equals the dense
+// forward's bit for bit; align = 1 packs ~12 % more real tokens per tile.
+int pack_chunk(const int32_t* lens, int first, int B, int cap_tiles, int max_seqs, int align, std::vector<int32_t>& row0,
                std::vector<uint8_t>& lo, std::vector<uint8_t>& hi, int* n_tiles_out) {
   constexpr int T = attn::kTile;
   std::vector<int> used;            // rows used per tile
@@ -717,7 +722,7 @@ int pack_chunk(const int32_t* lens, int first, int B, int cap_tiles, int max_seq
   auto push = [&](int tile) { const int f = T - used[tile]; next[tile] = head[f]; head[f] = tile; };
   int placed = 0;
   for (int b = first; b < B && placed < max_seqs; ++b) {
-    const int len = lens[b];
+    const int len = (lens[b] + align - 1) / align * align;   // rows of the slot
     int tile = -1;
     for (int f = len; f <= T; ++f)   // smallest free space that fits = fullest tile
       if (head[f] >= 0) { tile = head[f]; head[f] = next[tile]; break; }
@@ -753,13 +758,14 @@ int pack_chunk(const int32_t* lens, int first, int B, int cap_tiles, int max_seq
 }  // namespace
 
 // host-only view of the tile packing (tests): plans the FIRST chunk of lens[0..B) for a handle of `max_tokens`
-extern "C" int ance_dbg_pack_varlen(const int32_t* lens_host, int B, int max_tokens, int32_t* row0_out, uint8_t* lo_out,
-                                    uint8_t* hi_out, int* n_placed, int* n_tiles) {
+extern "C" int ance_dbg_pack_varlen(const int32_t* lens_host, int B, int max_tokens, int align, int32_t* row0_out,
+                                    uint8_t* lo_out, uint8_t* hi_out, int* n_placed, int* n_tiles) {
   ANCE_REQUIRE(lens_host && row0_out && n_placed && n_tiles && B > 0 && max_tokens >= attn::kTile, "ance_dbg_pack_varlen: bad arguments");
+  ANCE_REQUIRE(align == 1 || align == 16, "ance_dbg_pack_varlen: align must be 1 or 16");
   for (int b = 0; b < B; ++b) ANCE_REQUIRE(lens_host[b] >= 1 && lens_host[b] <= attn::kTile, "ance_dbg_pack_varlen: length %d out of range", lens_host[b]);
   std::vector<int32_t> row0;
   std::vector<uint8_t> lo, hi;
-  *n_placed = pack_chunk(lens_host, 0, B, max_tokens / attn::kTile, max_tokens / 16, row0, lo, hi, n_tiles);
+  *n_placed = pack_chunk(lens_host, 0, B, max_tokens / attn::kTile, max_tokens / 16, align, row0, lo, hi, n_tiles);
   memcpy(row0_out, row0.data(), row0.size() * 4);
   if (lo_out) memcpy(lo_out, lo.data(), lo.size());
   if (hi_out) memcpy(hi_out, hi.data(), hi.size());
@@ -785,7 +791,7 @@ extern "C" int ance_encoder_forward_varlen(ance_encoder_t e, const int32_t* ids_
   std::vector<uint8_t> lo, hi;
   for (int first = 0; first < B;) {
     int n_tiles = 0;
-    const int n = pack_chunk(lens_host, first, B, cap_tiles, max_seqs, row0, lo, hi, &n_tiles);
+    const int n = pack_chunk(lens_host, first, B, cap_tiles, max_seqs, e->varlen_align, row0, lo, hi, &n_tiles);
     // the plan arrays are read by the kernels of this chunk only; pageable cudaMemcpyAsync stages them before returning
     ANCE_CUDA(cudaMemcpyAsync(e->seq_row0, row0.data(), static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
     ANCE_CUDA(cudaMemcpyAsync(e->row_lo, lo.data(), lo.size(), cudaMemcpyHostToDevice, st));
@@ -805,6 +811,10 @@ extern "C" int ance_encoder_set_param(ance_encoder_t e, const char* name, double
   ANCE_REQUIRE(e != nullptr && name != nullptr, "ance_encoder_set_param: null argument");
   if (!strcmp(name, "prune_last_layer")) e->prune_last_layer = value != 0;
   else if (!strcmp(name, "ln_rows_per_warp")) g_ln_rows_per_warp = static_cast<int>(value);
+  else if (!strcmp(name, "varlen_align")) {
+    ANCE_REQUIRE(value == 1 || value == 16, "varlen_align must be 1 or 16");
+    e->varlen_align = static_cast<int>(value);
+  }
   else { ance::set_error("ance_encoder_set_param: unknown parameter '%s'", name); return ANCE_ERR_INVALID; }
   return ANCE_OK;
 }

@@ -40,17 +40,19 @@ struct WorkShape {
   // from HBM by the first pair is still in L2 when the last pair asks for it.  null = off.
   int* pace;
   int pace_window;
+  int pace_stride;   // clusters c, c + stride, c + 2 stride, ... sweep the same rows (1: all of them; n_splits: one wave of
+                     // (query tile, row range) items, item w on cluster w, range = w % n_splits)
 };
 
 // Publish this cluster's progress and wait (bounded: ~100 us, then go on regardless — the barrier is a bandwidth
 // optimisation, never a correctness requirement, and must not hang if the grid is not fully co-resident).
-static __device__ __noinline__ void pace_wait(int* pace, int window, int me, int n_clusters, int seq) {
+static __device__ __noinline__ void pace_wait(int* pace, int window, int me, int n_clusters, int stride, int seq) {
   volatile int* vp = pace;
   vp[me] = seq;
   const long long t0 = clock64();
   for (;;) {
     int mn = 0x7fffffff;
-    for (int c = 0; c < n_clusters; ++c) mn = min(mn, vp[c]);
+    for (int c = me % stride; c < n_clusters; c += stride) mn = min(mn, vp[c]);
     if (seq - mn <= window || clock64() - t0 > 200000ll) break;
   }
 }
@@ -138,7 +140,8 @@ tc05_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int a_row = (m_blk * CG + (int)cta_rank) * BM;
         for (int nb = nb0; nb < nb1; ++nb) {
           if (ws.pace != nullptr && leader && ((nb - nb0) & 7) == 0)
-            pace_wait(ws.pace, ws.pace_window, cluster_id, num_clusters, ((w - cluster_id) / num_clusters) * ws.num_n_blks + (nb - nb0));
+            pace_wait(ws.pace, ws.pace_window, cluster_id, num_clusters, ws.pace_stride,
+                      ((w - cluster_id) / num_clusters) * ws.num_n_blks + (nb - nb0));
           const int b_row = nb * BN + (int)cta_rank * Plan::kBRows;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1, 1);
@@ -299,6 +302,7 @@ inline WorkShape make_shape(int M, int N, int K, int BN, int CG, int n_splits /*
   ws.hint_a = ws.hint_b = 0;
   ws.pace = nullptr;
   ws.pace_window = 0;
+  ws.pace_stride = 1;
   return ws;
 }
 

@@ -740,15 +740,22 @@ int launch_coarse(ance_index* ix, const uint16_t* Q16, int64_t nq, int kprime, i
   if ((rc = ensure(&ix->cand_thr, &b, slots))) return rc;
   ix->cand_slots = a;
   if ((rc = ensure(&ix->cand_id, &ix->cand_ids, slots * out_cap))) return rc;
-  // Soft barrier between the sweeping CTA pairs (gemm_core.cuh): only when every work item sweeps the WHOLE corpus
-  // (n_splits == 1) and several pairs do so at once — then they share each corpus tile through L2 as long as they stay
-  // within `pace_window` tiles of each other.  Without it the pairs drift apart and every one of them streams the corpus
-  // from HBM by itself (ncu, round 1: 788 GB of DRAM reads for a 13.6 GB operand).
-  const int clusters = std::min(ws.num_m_blks * ws.n_splits, ctas / CG);
-  if (ws.n_splits == 1 && clusters > 1 && clusters <= kMaxPace && ix->pace_window > 0 && ws.num_n_blks > 4 * ix->pace_window) {
+  // Soft barrier between the sweeping CTA pairs (gemm_core.cuh): pairs that sweep the SAME corpus rows share each tile
+  // through L2 as long as they stay within `pace_window` tiles of each other.  Without it they drift apart and every one of
+  // them streams the rows from HBM by itself (ncu, round 1: 788 GB of DRAM reads for a 13.6 GB operand; measured round 2 at
+  // 18,944 and 75,776 queries: 910 -> 1213 TFLOP/s with the barrier).  Two shapes qualify: every item sweeps the whole
+  // corpus (n_splits == 1: all pairs pace each other), or one wave of (query tile, row range) items (pairs with the same
+  // range pace each other).
+  const int total_items = ws.num_m_blks * ws.n_splits;
+  const int clusters = std::min(total_items, ctas / CG);
+  const bool whole = ws.n_splits == 1 && clusters > 1;
+  const bool one_wave = ws.n_splits > 1 && ws.num_m_blks > 1 && total_items <= ctas / CG;
+  if ((whole || one_wave) && clusters <= kMaxPace && ix->pace_window > 0 && ws.n_blks_per_split > 4 * ix->pace_window) {
     ANCE_CUDA(cudaMemsetAsync(ix->pace, 0, kMaxPace * sizeof(int), st));
     ws.pace = ix->pace;
     ws.pace_window = ix->pace_window;
+    ws.pace_stride = whole ? 1 : ws.n_splits;
+    ws.hint_b = tc05::kEvictNormal;   // the tile is re-read by the other pairs of the group: keep it in L2
   }
   typename Ep::Params p;
   p.scratch_sc = ix->scratch_sc;

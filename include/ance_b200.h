@@ -144,14 +144,18 @@ int ance_encoder_forward(ance_encoder_t enc, const int32_t* ids_dev, const int32
  * are packed into 128-row attention tiles (a tile holds sequences of ANY lengths, none straddles a tile, every sequence
  * attends to its own tokens only), the linear layers and LayerNorms run on the packed token matrix, the CLS rows are
  * gathered for the last layer and the head.  lens_dev and lens_host hold the same B lengths, each in [1, L] (the tile
- * packing is planned on the host); B is unlimited (the call splits by the handle's max_tokens).  Embeddings equal those of
- * ance_encoder_forward up to fp32 summation order inside the softmax / P*V of a tile (tests: |diff| <= 2e-3). */
+ * packing is planned on the host); B is unlimited (the call splits by the handle's max_tokens).  With the default
+ * "varlen_align" = 1 the embeddings equal those of ance_encoder_forward up to fp32 summation order inside the softmax / P*V
+ * of a tile (a sequence's terms are grouped by its offset in the tile; tests: |diff| <= 1e-2, both within the gate of the
+ * fp32 reference); with "varlen_align" = 16 every sequence starts at a multiple of the tensor core's K step and the result
+ * is bit-identical to ance_encoder_forward and independent of the batch composition, at ~12 % fewer real tokens per tile. */
 int ance_encoder_forward_varlen(ance_encoder_t enc, const int32_t* ids_dev, const int32_t* lens_dev,
                                 const int32_t* lens_host, int B, int L, float* out_dev, void* stream);
 /* Tunables: "prune_last_layer" (default 1): in the last layer only token 0 of every sequence is read
  * downstream, so out-projection / FFN / LayerNorm run on those rows only (result-identical; bench.py reports
  * the executed FLOPs beside the algorithmic ones).  "ln_rows_per_warp" (1, 2 or 4; default 2, process-wide): rows a warp
- * of the LayerNorm kernel normalises side by side (bit-identical results; 2 is the fastest on B200). */
+ * of the LayerNorm kernel normalises side by side (bit-identical results; 2 is the fastest on B200).  "varlen_align" (1 | 16):
+ * see ance_encoder_forward_varlen. */
 int ance_encoder_set_param(ance_encoder_t enc, const char* name, double value);
 /* Input / output validation, deferred so that forward stays asynchronous: synchronises `stream` and returns
  * ANCE_ERR_INVALID if any forward since the last check saw a token id outside [0, vocab_size) or a position
@@ -183,7 +187,7 @@ int ance_profile_read(double* ms_by_class, int64_t* launches_by_class, int n, in
 /* Host-only: the tile plan ance_encoder_forward_varlen makes for the first chunk of lens_host[0..B) on a handle created with
  * `max_tokens`: row0_out[i] = packed row of sequence i's first token (i < *n_placed), lo/hi_out [*n_tiles * 128] = own-sequence
  * key range of every packed row (may be null). */
-int ance_dbg_pack_varlen(const int32_t* lens_host, int B, int max_tokens, int32_t* row0_out, uint8_t* lo_out,
+int ance_dbg_pack_varlen(const int32_t* lens_host, int B, int max_tokens, int align, int32_t* row0_out, uint8_t* lo_out,
                          uint8_t* hi_out, int* n_placed, int* n_tiles);
 int ance_dbg_gemm(const void* A_dev, const void* B_dev, int M, int N, int K, int fmt, int variant,
                   const float* bias_dev, const void* residual_bf16_dev, int act, void* C_bf16_dev,
