@@ -65,6 +65,7 @@ SIGNATURES = {
     "ance_index_reset": (C.c_int, [C.c_void_p]),
     "ance_index_ntotal": (C.c_int64, [C.c_void_p]),
     "ance_index_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ance_index_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ance_index_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_void_p]),
     "ance_index_search_exact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,

@@ -74,20 +74,29 @@ __device__ __forceinline__ T* shfl_ptr(T* p, int src) {
 // ------------------------------------------------------------------------------------------------
 // 1. fp32 -> 16-bit operand rows, with the norms the certificate needs
 // ------------------------------------------------------------------------------------------------
+// mu (index rows only, may be null): the rows are CENTRED before rounding, x' = x - mu.  <q, x> = <q, x - mu> + <q, mu> and
+// the second term is the same for every row, so the ranking is unchanged while every norm in the certificate's error bound
+// becomes that of the centred row — embeddings that share a large common component (anisotropic BERT-style outputs, an
+// untrained / collapsed encoder) would otherwise spend the 16-bit significand on the component that cannot change the order.
 template <bool kBF16>
 __global__ void quantize_rows_kernel(const float* __restrict__ X, uint16_t* __restrict__ X16, int64_t n, int d,
-                                     float* __restrict__ norm_hat, float* __restrict__ norm_delta,
-                                     unsigned int* __restrict__ max_stats, int* __restrict__ err_flag) {
+                                     const float* __restrict__ mu, float* __restrict__ norm_hat,
+                                     float* __restrict__ norm_delta, unsigned int* __restrict__ max_stats,
+                                     int* __restrict__ err_flag) {
   // err_flag: set to 1 when a value is non-finite after rounding (fp16 overflow, or inf / NaN in the input)
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const float* x = X + row * d;
   uint16_t* o = X16 + row * d;
-  float sh = 0.f, sd = 0.f;
+  float sh = 0.f, sd = 0.f, sx = 0.f;
   bool bad = false;
   for (int i = lane * 4; i < d; i += 128) {  // d % 4 == 0 (checked on the host)
     float4 v = __ldg(reinterpret_cast<const float4*>(x + i));
+    if (mu) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mu + i));
+      v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+    }
     float a[4] = {v.x, v.y, v.z, v.w};
     uint16_t q[4];
 #pragma unroll
@@ -106,6 +115,7 @@ __global__ void quantize_rows_kernel(const float* __restrict__ X, uint16_t* __re
       sh = fmaf(back, back, sh);
       const float e = a[t] - back;
       sd = fmaf(e, e, sd);
+      sx = fmaf(a[t], a[t], sx);
     }
     uint2 pk;
     pk.x = static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 16);
@@ -116,11 +126,13 @@ __global__ void quantize_rows_kernel(const float* __restrict__ X, uint16_t* __re
   for (int s = 16; s > 0; s >>= 1) {
     sh += __shfl_xor_sync(0xffffffffu, sh, s);
     sd += __shfl_xor_sync(0xffffffffu, sd, s);
+    sx += __shfl_xor_sync(0xffffffffu, sx, s);
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0 && err_flag) atomicExch(err_flag, 1);
   if (lane == 0) {
     // round the bounds up a little: they are upper bounds in the certificate
-    const float nh = sqrtf(sh) * 1.00001f, nd = sqrtf(sd) * 1.00001f;
+    // (the fp32 subtraction x - mu is itself rounded: at most 2^-24 |x - mu| per element, charged to the delta norm)
+    const float nh = sqrtf(sh) * 1.00001f, nd = (sqrtf(sd) + (mu ? 1.2e-7f * sqrtf(sx) : 0.f)) * 1.00001f;
     if (norm_hat) norm_hat[row] = nh;
     if (norm_delta) norm_delta[row] = nd;
     if (max_stats) {  // non-negative floats order like their bit patterns
@@ -128,6 +140,21 @@ __global__ void quantize_rows_kernel(const float* __restrict__ X, uint16_t* __re
       atomicMax(&max_stats[1], __float_as_uint(nd));
     }
   }
+}
+
+// column sums of a slab of rows (fp64), one atomicAdd per (block, column); then mu = sums / n
+constexpr int kMeanSlab = 4096;
+__global__ void __launch_bounds__(256) column_sum_kernel(const float* __restrict__ X, int64_t n, int d, double* __restrict__ sums) {
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kMeanSlab, r1 = min(n, r0 + kMeanSlab);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    double acc = 0.0;
+    for (int64_t r = r0; r < r1; ++r) acc += static_cast<double>(__ldg(X + r * d + c));
+    atomicAdd(sums + c, acc);
+  }
+}
+__global__ void finalize_mean_kernel(const double* __restrict__ sums, int64_t n, int d, float* __restrict__ mu) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < d) mu[c] = static_cast<float>(sums[c] / static_cast<double>(n));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -345,7 +372,8 @@ struct RescoreParams {
   int n_splits, cand_stride, k;   // cand_stride = EpTopK out_cap
   const float* qn_hat;
   const float* qn_delta;
-  const unsigned int* pstats;  // [0] max ||p^||, [1] max ||p - p^|| (float bits)
+  const unsigned int* pstats;  // [0] max ||p^||, [1] max ||p - p^|| (float bits) of the CENTRED rows
+  const float* mu;             // the centre subtracted from every index row before rounding (null: none)
   float accum_rel;             // bound on the tensor core's accumulation error / (||q^|| ||p^||), see coarse_rescore_pass
   float* D;
   int64_t* I;
@@ -416,6 +444,16 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   __syncthreads();
   const int m = offs[p.n_splits];
   for (int i = threadIdx.x; i < p.sort_n; i += blockDim.x) keys[i] = 0ull;
+  // <q, mu> in fp64: what separates the coarse (centred) scores from the exact ones, identically for every row
+  __shared__ double s_qmu[8];
+  {
+    double part = 0.0;
+    if (p.mu)
+      for (int i = threadIdx.x; i < p.d; i += blockDim.x) part = fma(static_cast<double>(qs[i]), static_cast<double>(__ldg(p.mu + i)), part);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(0xffffffffu, part, s);
+    if (lane == 0) s_qmu[warp] = part;
+  }
   __syncthreads();
   constexpr int kNB = 4;
   const bool wide = p.d == 768;   // the path's dimension (models.py:145-146); other dims take the one-row loop
@@ -461,10 +499,17 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
     // |coarse_j - <q, p_j>| <= eps for EVERY row j (Cauchy-Schwarz on the operand rounding + the accumulation bound);
     // the factor covers the fp32 roundings of this expression itself (norms are already rounded up)
     const float eps = (qd * maxp + qn * maxdp + qd * maxdp + p.accum_rel * qn * maxp) * 1.0001f;
+    // A row that is not a candidate has centred coarse score <= thr, hence exact score <= thr + eps + <q, mu>.  The k-th
+    // exact score is an fp64 dot product rounded to fp32: the unrounded value is >= sk_lo.  Compared in fp64.
+    double qmu = 0.0;
+    for (int w2 = 0; w2 < nwarps; ++w2) qmu += s_qmu[w2];
+    const double qmu_up = qmu + fabs(qmu) * 1.0e-12;
+    const double sk = (m >= p.k) ? static_cast<double>(key_score(keys[p.k - 1])) : -INFINITY;
+    const double sk_lo = sk - fabs(sk) * 1.2e-7;
     bool certified;
     if (thr == -INFINITY) certified = true;       // every row of the index was a candidate
     else if (m < p.k) certified = false;          // cannot happen (thr finite => >= k candidates passed it)
-    else certified = (__fadd_ru(thr, eps) < key_score(keys[p.k - 1]));
+    else certified = (static_cast<double>(thr) + static_cast<double>(eps) + qmu_up < sk_lo);
     atomicAdd(&p.counters[1], m);
     atomicMax(p.max_eps, __float_as_uint(eps));
     if (!certified) {
@@ -473,9 +518,8 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
       if (p.flagged_thr) {
         // Next tier starts from t < s_k - eps: every row whose exact score reaches s_k (the k-th exact score found so
         // far, a lower bound of the final one) has coarse score >= s_k - eps > t, i.e. passes the filter.
-        const float sk = (m >= p.k) ? key_score(keys[p.k - 1]) : -INFINITY;
-        const float x = __fsub_rd(sk, eps);
-        p.flagged_thr[slot] = (sk == -INFINITY) ? -INFINITY : __fsub_rd(x, fmaxf(fabsf(sk), eps) * 1.0e-6f);
+        const float x = __double2float_rd(sk_lo - qmu_up - static_cast<double>(eps));   // in centred coarse-score units
+        p.flagged_thr[slot] = (m < p.k) ? -INFINITY : __fsub_rd(x, fmaxf(fabsf(x), eps) * 1.0e-6f);
       }
     }
   }
@@ -646,6 +690,11 @@ struct ance_index {
   bool owns_p32 = true;      // false: caller-owned storage (ance_index_create_over)
   uint16_t* P16 = nullptr;   // [cap, dim]
   unsigned int* pstats = nullptr;  // [2]
+  float* mu = nullptr;             // [dim] centre of the rows (see quantize_rows_kernel)
+  double* colsum = nullptr;        // [dim]
+  bool dirty = false;              // rows were added / the format changed since the 16-bit operands were (re)built
+  bool centred = false;
+  int center = 1;                  // tunable "center": subtract the column mean before rounding
   // tunables
   int kprime = 0, n_splits = 0, cta_group = 2, max_ctas = 0, exact_fallback = 1, tier2 = 1, pace_window = 16;
   // workspace (grown lazily)
@@ -874,6 +923,7 @@ int coarse_rescore_pass(ance_index* ix, const uint16_t* Q16, const float* q_f32,
   rp.qn_hat = ix->qn_hat;
   rp.qn_delta = ix->qn_delta;
   rp.pstats = ix->pstats;
+  rp.mu = ix->centred ? ix->mu : nullptr;
   // Accumulation error of the coarse score c = fl(sum_i q^_i p^_i) on the tensor core.  The 16-bit x 16-bit products
   // are exact in fp32; what is unspecified is how tcgen05.mma adds them (PTX: "precision at least that of fp32", order
   // and rounding implementation-defined; published measurements of earlier generations: truncation, block adds of
@@ -928,7 +978,9 @@ int create_common(int dim, int64_t capacity_rows, int operand_fmt, float* extern
   cudaError_t e3 = cudaMalloc(&ix->pstats, 2 * sizeof(unsigned int));
   cudaError_t e4 = cudaMalloc(&ix->pace, kMaxPace * sizeof(int));
   cudaError_t e5 = cudaMalloc(&ix->counters, kNumCounters * sizeof(int));
-  if (e1 || e2 || e3 || e4 || e5) {
+  cudaError_t e6 = cudaMalloc(&ix->mu, static_cast<size_t>(dim) * sizeof(float));
+  cudaError_t e7 = cudaMalloc(&ix->colsum, static_cast<size_t>(dim) * sizeof(double));
+  if (e1 || e2 || e3 || e4 || e5 || e6 || e7) {
     ance::set_error("ance_index_create: cudaMalloc failed for %lld x %d rows", (long long)capacity_rows, dim);
     ance_index_destroy(ix);
     return ANCE_ERR_NOMEM;
@@ -939,18 +991,35 @@ int create_common(int dim, int64_t capacity_rows, int operand_fmt, float* extern
   return ANCE_OK;
 }
 
-int quantize_rows(ance_index* ix, int64_t first, int64_t n, cudaStream_t st) {
-  const float* src = ix->P32 + static_cast<size_t>(first) * ix->dim;
-  uint16_t* dst16 = ix->P16 + static_cast<size_t>(first) * ix->dim;
+// (Re)build the 16-bit operands of every row from the fp32 rows: column mean -> centre -> round, norm maxima, range flag.
+// Runs once per index state (lazily, at the first search after rows were added): ~45 GB of HBM traffic for 8.84M rows,
+// about 10 ms — nothing next to the encode that produced the rows — and it lets the centre be the mean of ALL rows.
+int prepare_operands(ance_index* ix, cudaStream_t st) {
+  if (!ix->dirty) return ANCE_OK;
+  const int64_t n = ix->n;
+  ANCE_CUDA(cudaMemsetAsync(ix->pstats, 0, 2 * sizeof(unsigned int), st));
+  ANCE_CUDA(cudaMemsetAsync(ix->counters + kCntRowErr, 0, sizeof(int), st));
+  ance::ProfScope ps(ance::kClsQuant, st);
+  ix->centred = ix->center && n >= 256;
+  if (ix->centred) {
+    ANCE_CUDA(cudaMemsetAsync(ix->colsum, 0, static_cast<size_t>(ix->dim) * sizeof(double), st));
+    column_sum_kernel<<<static_cast<unsigned>((n + kMeanSlab - 1) / kMeanSlab), 256, 0, st>>>(ix->P32, n, ix->dim, ix->colsum);
+    finalize_mean_kernel<<<(ix->dim + 255) / 256, 256, 0, st>>>(ix->colsum, n, ix->dim, ix->mu);
+    ANCE_CUDA(cudaGetLastError());
+    ance::count_launch(2);
+  }
+  const float* mu = ix->centred ? ix->mu : nullptr;
   const int wpb = 8;
   const unsigned blocks = static_cast<unsigned>((n + wpb - 1) / wpb);
-  ance::ProfScope ps(ance::kClsQuant, st);
-  if (ix->fmt == ANCE_FMT_BF16)
-    quantize_rows_kernel<true><<<blocks, wpb * 32, 0, st>>>(src, dst16, n, ix->dim, nullptr, nullptr, ix->pstats, ix->counters + kCntRowErr);
-  else
-    quantize_rows_kernel<false><<<blocks, wpb * 32, 0, st>>>(src, dst16, n, ix->dim, nullptr, nullptr, ix->pstats, ix->counters + kCntRowErr);
-  ANCE_CUDA(cudaGetLastError());
-  ance::count_launch(1);
+  if (n > 0) {
+    if (ix->fmt == ANCE_FMT_BF16)
+      quantize_rows_kernel<true><<<blocks, wpb * 32, 0, st>>>(ix->P32, ix->P16, n, ix->dim, mu, nullptr, nullptr, ix->pstats, ix->counters + kCntRowErr);
+    else
+      quantize_rows_kernel<false><<<blocks, wpb * 32, 0, st>>>(ix->P32, ix->P16, n, ix->dim, mu, nullptr, nullptr, ix->pstats, ix->counters + kCntRowErr);
+    ANCE_CUDA(cudaGetLastError());
+    ance::count_launch(1);
+  }
+  ix->dirty = false;
   return ANCE_OK;
 }
 
@@ -971,7 +1040,7 @@ extern "C" int ance_index_destroy(ance_index_t ix) {
   if (!ix) return ANCE_OK;
   void* ptrs[] = {ix->owns_p32 ? ix->P32 : nullptr, ix->P16, ix->pstats, ix->Q16, ix->qn_hat, ix->qn_delta, ix->scratch_sc,
                   ix->scratch_id, ix->cand_id, ix->cand_cnt, ix->cand_thr, ix->flagged, ix->flagged_thr, ix->counters,
-                  ix->chunk_keys, ix->flagged2, ix->Q16b, ix->pace};
+                  ix->chunk_keys, ix->flagged2, ix->Q16b, ix->pace, ix->mu, ix->colsum};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ix;
@@ -981,6 +1050,7 @@ extern "C" int ance_index_destroy(ance_index_t ix) {
 extern "C" int ance_index_reset(ance_index_t ix) {
   ANCE_REQUIRE(ix != nullptr, "ance_index_reset: null handle");
   ix->n = 0;
+  ix->dirty = false;
   ANCE_CUDA(cudaMemset(ix->pstats, 0, 2 * sizeof(unsigned int)));
   ANCE_CUDA(cudaMemset(ix->counters, 0, kNumCounters * sizeof(int)));
   return ANCE_OK;
@@ -1001,9 +1071,16 @@ extern "C" int ance_index_add(ance_index_t ix, const float* rows_dev, int64_t n,
   float* dst = ix->P32 + static_cast<size_t>(ix->n) * ix->dim;
   if (dst != rows_dev)   // rows produced in place (the encoder wrote straight into the index storage): no copy
     ANCE_CUDA(cudaMemcpyAsync(dst, rows_dev, static_cast<size_t>(n) * ix->dim * 4, cudaMemcpyDeviceToDevice, st));
-  if ((rc = quantize_rows(ix, ix->n, n, st))) return rc;
   ix->n += n;
+  ix->dirty = true;      // the 16-bit operands are (re)built from all rows by the next ance_index_prepare / search
   return ANCE_OK;
+}
+
+extern "C" int ance_index_prepare(ance_index_t ix, void* stream) {
+  ANCE_REQUIRE(ix != nullptr, "ance_index_prepare: null handle");
+  int rc = check_handle_device(ix, "ance_index_prepare");
+  if (rc) return rc;
+  return prepare_operands(ix, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ance_index_set_param(ance_index_t ix, const char* name, double value) {
@@ -1023,12 +1100,10 @@ extern "C" int ance_index_set_param(ance_index_t ix, const char* name, double va
     if (rc) return rc;
     if (v != ix->fmt) {
       ix->fmt = v;
-      ANCE_CUDA(cudaMemset(ix->pstats, 0, 2 * sizeof(unsigned int)));
-      ANCE_CUDA(cudaMemset(ix->counters + kCntRowErr, 0, sizeof(int)));
-      if (ix->n > 0 && (rc = quantize_rows(ix, 0, ix->n, nullptr))) return rc;
-      ANCE_CUDA(cudaDeviceSynchronize());
+      ix->dirty = true;
     }
   }
+  else if (!strcmp(name, "center")) { ix->center = v != 0; ix->dirty = true; }
   else { ance::set_error("ance_index_set_param: unknown parameter '%s'", name); return ANCE_ERR_INVALID; }
   return ANCE_OK;
 }
@@ -1080,6 +1155,7 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
     ix->stats.n_uncertified = nq;
     return ance_index_search_exact(ix, q_dev, nq, k, D_dev, I_dev, row_offset, stream);
   }
+  if ((rc = prepare_operands(ix, st))) return rc;
   // --- 1. quantize queries
   {
     size_t a = static_cast<size_t>(ix->q_cap) * ix->dim, b = ix->q_cap, c = ix->q_cap;
@@ -1096,9 +1172,9 @@ extern "C" int ance_index_search(ance_index_t ix, const float* q_dev, int64_t nq
   const unsigned qblocks = static_cast<unsigned>((nq + 7) / 8);
   ance::prof_begin(ance::kClsQuant, st);
   if (ix->fmt == ANCE_FMT_BF16)
-    quantize_rows_kernel<true><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, ix->qn_hat, ix->qn_delta, nullptr, ix->counters + kCntQueryErr);
+    quantize_rows_kernel<true><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, nullptr, ix->qn_hat, ix->qn_delta, nullptr, ix->counters + kCntQueryErr);
   else
-    quantize_rows_kernel<false><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, ix->qn_hat, ix->qn_delta, nullptr, ix->counters + kCntQueryErr);
+    quantize_rows_kernel<false><<<qblocks, 256, 0, st>>>(q_dev, ix->Q16, nq, ix->dim, nullptr, ix->qn_hat, ix->qn_delta, nullptr, ix->counters + kCntQueryErr);
   ance::prof_end(ance::kClsQuant, st);
   ANCE_CUDA(cudaGetLastError());
   ance::count_launch(1);

@@ -221,6 +221,7 @@ class B200Backend:
                                 operand=self.args.search_operand)
             index.add(passages)
         self.index = index
+        index.prepare()     # centred 16-bit operands of all rows (otherwise done inside the first search)
         return lambda q, k, row_offset: index.search_device(q, k, row_offset=row_offset)
 
 

@@ -122,6 +122,13 @@ class IndexFlatIP:
             if step != n:   # host input: the pinned staging tensors must outlive their copies
                 torch.cuda.current_stream().synchronize()
 
+    def prepare(self):
+        """Build the coarse pass's 16-bit operands from all rows added so far (centred on their mean, rounded to the
+        operand format).  search() does it on demand; calling it keeps the cost out of the first search."""
+        if self._h is not None and self.ntotal:
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.ance_index_prepare(self._h, _lib.current_stream()))
+
     # -- search ------------------------------------------------------------------------------------
     def search_device(self, q: torch.Tensor, k: int, row_offset: int = 0, exact: bool = False
                       ) -> Tuple[torch.Tensor, torch.Tensor]:

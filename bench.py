@@ -403,7 +403,8 @@ def run_b200(args, wl):
     def step_value():
         step_index.reset()
         encode_passages_fast(p_ids_d, p_len_d)
-        step_index.add(step_rows)
+        step_index.add(step_rows)          # in place: the rows were written into the index's own storage
+        step_index.prepare()               # column mean + centred 16-bit operands + norm statistics of the added rows
         q = model.query_emb(q_ids_d, q_ids_d != 0) if mask_form else model.encode_lens(q_ids_d, q_len_d)
         if world > 1:
             q_all = torch.empty((qb * world, DIM), dtype=torch.float32, device=dev)
@@ -421,6 +422,7 @@ def run_b200(args, wl):
         qi, qm = q_ids_h.to(dev, non_blocking=True), q_mask_h.to(dev, non_blocking=True)
         emb = model.body_emb(pi.long(), pm.long())
         step_index.add(emb.reshape(pb * C, DIM))
+        step_index.prepare()
         q = model.query_emb(qi.long(), qm.long())
         if world > 1:
             q_all = torch.empty((qb * world, DIM), dtype=torch.float32, device=dev)

@@ -307,3 +307,27 @@ def test_index_over_caller_storage_adds_in_place():
     assert (I == Io).all() and (D == Do).all()
     with pytest.raises(ValueError):
         IndexFlatIP(768, storage=torch.empty((10, 64), device="cuda"))
+
+
+def test_centering_certifies_concentrated_embeddings():
+    """Embeddings that share a large common component (anisotropic BERT-style outputs; an untrained / collapsed encoder —
+    what the seeded-random checkpoints of this repo's own full-refresh runs produce): the score differences that decide the
+    ranking are tiny next to the scores.  The index centres its rows before rounding them to 16 bits, so the certificate's
+    error bound scales with the spread, not with the common component: everything certifies at tier 1; without the centring
+    the same data falls through to the brute force."""
+    rng = np.random.default_rng(61)
+    n, nq, k = 200_000, 256, 100
+    common = _ln_rows(rng, 1, 768, clustered=False)
+    P = (common + 0.1 * rng.standard_normal((n, 768))).astype(np.float32)
+    Q = (common + 0.1 * np.random.default_rng(62).standard_normal((nq, 768))).astype(np.float32)
+    idx = _index(P, "fp16", n_splits=1)
+    D, I = idx.search(Q, k)
+    st = idx.stats()
+    Do, Io = flat_ip_oracle.search(P, Q[:48], k)
+    assert (I[:48] == Io).all() and (D[:48] == Do).all()
+    assert st["n_tier2"] == 0 and st["n_uncertified"] == 0 and st["max_eps"] < 0.1, st
+    raw = _index(P, "fp16", n_splits=1, center=0)
+    D2, I2 = raw.search(Q, k)
+    st2 = raw.stats()
+    assert (I2 == I).all() and (D2 == D).all()                 # still exact, the expensive way
+    assert st2["max_eps"] > 5 * st["max_eps"] and st2["n_tier2"] > nq // 2, (st, st2)
