@@ -270,9 +270,32 @@ class _Staging:
         self.job = None
 
 
+_STAGING_CACHE: Dict[tuple, list] = {}     # (rows, k, with_scores, pinned) -> two buffers, kept across calls
+_MERGE_POOL = None
+
+
+def _staging(rows: int, k: int, with_scores: bool, pin: bool):
+    key = (rows, k, with_scores, pin)
+    if key not in _STAGING_CACHE:
+        if len(_STAGING_CACHE) > 8:
+            _STAGING_CACHE.clear()
+        _STAGING_CACHE[key] = [_Staging(rows, k, with_scores, pin) for _ in range(2)]
+    for st in _STAGING_CACHE[key]:
+        st.job = None
+    return _STAGING_CACHE[key]
+
+
+def _merge_pool():
+    global _MERGE_POOL
+    if _MERGE_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _MERGE_POOL = ThreadPoolExecutor(max_workers=1)
+    return _MERGE_POOL
+
+
 def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch.Tensor, k: int,
-                   merge_threads: int = 0, query_block: int = QUERY_BLOCK, gather_to_rank0: bool = True
-                   ) -> Optional[np.ndarray]:
+                   merge_threads: int = 0, query_block: int = QUERY_BLOCK, gather_to_rank0: bool = True,
+                   row_offset: Optional[int] = None) -> Optional[np.ndarray]:
     """Every rank searches its own rows for ALL queries; the per-shard top-k lists of a query are merged on the rank
     that OWNS the query, so the merge (and its device->host copy) is spread over all ranks instead of serialised on
     rank 0, and it overlaps the search of the next query block:
@@ -283,20 +306,19 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
             async D2H into pinned staging  ->  host k-way merge (C++, worker thread)      || next block's search
 
     Returns I [nq, k] (global rows, merged order) on rank 0 and None elsewhere; with gather_to_rank0=False every rank
-    gets the merged lists of the queries it owns as (I_own [n_own, k], own_query_numbers)."""
-    from concurrent.futures import ThreadPoolExecutor
+    gets the merged lists of the queries it owns as (I_own [n_own, k], own_query_numbers).  row_offset: global number
+    of this rank's first row (= rows of the ranks before it); computed with one small all-gather when not given."""
     from ..search import merge_topk_host
     W, rank = _world()
     dev = queries_all.device
     cuda = dev.type == "cuda"
-    sizes = _shard_sizes(n_local_rows, dev)
-    offset = int(sum(sizes[:rank]))
+    offset = int(row_offset) if row_offset is not None else int(sum(_shard_sizes(n_local_rows, dev)[:rank]))
     nq = int(queries_all.shape[0])
     QB = max(W, (max(1, min(query_block, nq)) + W - 1) // W * W)      # a multiple of W: equal all-to-all splits
     part = QB // W
     side = torch.cuda.Stream(device=dev) if cuda else None
-    stage = [_Staging(QB, k, W > 1, cuda) for _ in range(2)]
-    pool = ThreadPoolExecutor(max_workers=1)
+    stage = _staging(QB, k, W > 1, cuda)
+    pool = _merge_pool()
     own_I: List[np.ndarray] = []
     own_q: List[np.ndarray] = []
 
@@ -348,7 +370,6 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
     for st in stage:
         if st.job is not None:
             st.job.result()
-    pool.shutdown()
     I_own = np.concatenate(own_I) if own_I else np.empty((0, k), dtype=np.int64)
     q_own = np.concatenate(own_q) if own_q else np.empty((0,), dtype=np.int64)
     if not gather_to_rank0:
@@ -431,12 +452,13 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
     q_all, query_embedding2id = all_gather_rows(q_emb), all_gather_ids(q_ids, device)
     t = lap("all_gather_s", t)
 
-    dev_I = sharded_search(local_search, p_emb.shape[0], dev_all, 100)               # run_ann_data_gen.py:276
+    row_offset = int(sum(_shard_sizes(p_emb.shape[0], device)[:_world()[1]]))
+    dev_I = sharded_search(local_search, p_emb.shape[0], dev_all, 100, row_offset=row_offset)   # run_ann_data_gen.py:276
     t = lap("search_dev_s", t)
     q_start, q_end = postprocess.query_chunk(q_all.shape[0], output_num, args.ann_chunk_factor)
     q_all, query_embedding2id = q_all[q_start:q_end], query_embedding2id[q_start:q_end]
     logger.info("Chunked {} query from {}".format(q_end - q_start, q_emb.shape[0]))
-    I = sharded_search(local_search, p_emb.shape[0], q_all.contiguous(), args.topk_training)  # :303
+    I = sharded_search(local_search, p_emb.shape[0], q_all.contiguous(), args.topk_training, row_offset=row_offset)  # :303
     t = lap("search_train_s", t)
     t_search = time.time()
     if not is_first_worker():

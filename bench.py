@@ -372,6 +372,7 @@ def run_b200(args, wl):
     # this rank's shard of the synthetic corpus, resident for the whole run
     n_index = wl["n_index"]
     n_local = len(range(rank, n_index, world))
+    row_offset = sum(len(range(r, n_index, world)) for r in range(rank))   # global number of this rank's first row
     index = IndexFlatIP(DIM, capacity=n_local, device=dev, operand=args.search_operand)
     for x in synth_index_rows(n_local, DIM, dev, 1234 + rank, wl["index_kind"]):
         index.add(x)
@@ -411,7 +412,7 @@ def run_b200(args, wl):
             dist.all_gather_into_tensor(q_all, q.contiguous())
         else:
             q_all = q
-        return sharded_search(local_search, n_local, q_all.contiguous(), k)    # numpy labels on rank 0
+        return sharded_search(local_search, n_local, q_all.contiguous(), k, row_offset=row_offset)    # numpy labels on rank 0
 
     def step_e2e():
         """The calls a user of the reference makes (run_ann_data_gen.py:172-180,269-303), host buffers in, numpy out:
@@ -427,7 +428,7 @@ def run_b200(args, wl):
         if world > 1:
             q_all = torch.empty((qb * world, DIM), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(q_all, q.contiguous())
-            return sharded_search(local_search, n_local, q_all, k)
+            return sharded_search(local_search, n_local, q_all, k, row_offset=row_offset)
         _, I = index.search(q.cpu().numpy(), k)
         return I
 
