@@ -89,7 +89,7 @@ def main():
     argv = ["--data_dir", data, "--training_dir", os.path.join(a.work_dir, "no_training_dir"), "--init_model_dir", ckpt,
             "--model_type", "rdot_nll", "--output_dir", out, "--cache_dir", os.path.join(a.work_dir, "cache"),
             "--end_output_num", "0", "--max_seq_length", "128", "--max_query_length", "64",
-            "--per_gpu_eval_batch_size", "128", "--topk_training", str(a.topk_training), "--negative_sample",
+            "--per_gpu_eval_batch_size", "16", "--topk_training", str(a.topk_training), "--negative_sample",
             str(a.negative_sample), "--ann_chunk_factor", "1", "--seed", "0"]
     if a.lengths == "full":
         argv.append("--no_length_buckets")   # nothing to bucket: every passage is 128 tokens (queries keep their padding too)
