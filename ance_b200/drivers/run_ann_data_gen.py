@@ -164,7 +164,11 @@ class B200Backend:
         multi = (not is_query) and hasattr(self.model, "encode_lens_multi_chunk") and L > 512
         C = (L // 512) if multi else 1
         B = args.per_gpu_eval_batch_size
-        per = max(B, (args.encode_batch_tokens // L) // B * B)  # super-batch, a multiple of the reference batch
+        # super-batch = what one encoder pass holds.  Only the MaxP row layout depends on the reference's batch size
+        # (chunk-major per `per_gpu_eval_batch_size` documents, run_ann_data_gen.py:183-186): there it must be a multiple
+        # of B; elsewhere B has no effect on the result and the pass is filled completely (592 x 128 tokens = whole waves
+        # of 256-row GEMM tiles on 148 SMs).
+        per = max(B, (args.encode_batch_tokens // L) // B * B) if multi else max(1, args.encode_batch_tokens // L)
         bucketed = self.mask_mode != "nonzero" and not multi and getattr(args, "length_buckets", True)
         varlen = bucketed and L <= 128 and getattr(args, "varlen", True) and hasattr(self.model, "encode_lens_varlen")
         if bucketed:
