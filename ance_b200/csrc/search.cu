@@ -143,9 +143,9 @@ __global__ void quantize_rows_kernel(const float* __restrict__ X, uint16_t* __re
 }
 
 // column sums of a slab of rows (fp64), one atomicAdd per (block, column); then mu = sums / n
-constexpr int kMeanSlab = 4096;
-__global__ void __launch_bounds__(256) column_sum_kernel(const float* __restrict__ X, int64_t n, int d, double* __restrict__ sums) {
-  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kMeanSlab, r1 = min(n, r0 + kMeanSlab);
+__global__ void __launch_bounds__(256) column_sum_kernel(const float* __restrict__ X, int64_t n, int d, int slab,
+                                                         double* __restrict__ sums) {
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * slab, r1 = min(n, r0 + slab);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     double acc = 0.0;
     for (int64_t r = r0; r < r1; ++r) acc += static_cast<double>(__ldg(X + r * d + c));
@@ -1003,7 +1003,9 @@ int prepare_operands(ance_index* ix, cudaStream_t st) {
   ix->centred = ix->center && n >= 256;
   if (ix->centred) {
     ANCE_CUDA(cudaMemsetAsync(ix->colsum, 0, static_cast<size_t>(ix->dim) * sizeof(double), st));
-    column_sum_kernel<<<static_cast<unsigned>((n + kMeanSlab - 1) / kMeanSlab), 256, 0, st>>>(ix->P32, n, ix->dim, ix->colsum);
+    // rows per block: enough blocks to fill the machine for a small index, few enough atomics (n / slab per column) for a big one
+    const int slab = static_cast<int>(std::min<int64_t>(4096, std::max<int64_t>(32, n / (8 * gemm::sm_count()))));
+    column_sum_kernel<<<static_cast<unsigned>((n + slab - 1) / slab), 256, 0, st>>>(ix->P32, n, ix->dim, slab, ix->colsum);
     finalize_mean_kernel<<<(ix->dim + 255) / 256, 256, 0, st>>>(ix->colsum, n, ix->dim, ix->mu);
     ANCE_CUDA(cudaGetLastError());
     ance::count_launch(2);

@@ -89,16 +89,19 @@ def test_duplicates_and_ties_are_ordered_by_row():
 
 
 def test_uncertified_queries_fall_back_to_exact():
-    """Rows that differ by less than the 16-bit operand rounding cannot be separated by the coarse pass:
-    the certificate must fail and the exact brute-force path must still return the oracle's answer."""
+    """Thousands of EXACTLY equal rows at the top of every ranking: no 16-bit pass can separate them (thr == s_k), the
+    tier-2 pass from the threshold s_k - eps lets all of them through and its reservoir overflows, so the exact
+    brute-force path must produce the oracle's answer (ties in ascending row order)."""
     rng = np.random.default_rng(8)
     base = _ln_rows(rng, 1, 768)
-    P = np.repeat(base, 8192, axis=0) + 1e-4 * rng.standard_normal((8192, 768)).astype(np.float32)
-    Q = _ln_rows(np.random.default_rng(9), 32, 768)
+    P = _ln_rows(np.random.default_rng(80), 16384, 768)
+    P[::2] = base                                      # 8192 identical rows, interleaved with ordinary ones
+    Q = (base * 1.0 + 0.05 * _ln_rows(np.random.default_rng(9), 32, 768)).astype(np.float32)   # queries near the duplicated row
     idx = _index(P)
     D, I = idx.search(Q, 50)
     Do, Io = flat_ip_oracle.search_bruteforce(P, Q, 50)
     assert (I == Io).all() and (D == Do).all()
+    assert (I[:, :50] % 2 == 0).all() and (np.diff(I, axis=1) > 0).all()     # the duplicates, smallest rows first
     assert idx.stats()["n_uncertified"] > 0
 
 
