@@ -74,6 +74,8 @@ SIGNATURES = {
     "ance_index_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "ance_merge_topk_host": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_int]),
+    "ance_write_training_data_host": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
     "ance_encoder_create": (C.c_int, [C.POINTER(EncoderConfig), C.POINTER(EncoderWeights), C.c_int,
                                       C.POINTER(C.c_void_p)]),
     "ance_encoder_destroy": (C.c_int, [C.c_void_p]),

@@ -82,3 +82,57 @@ extern "C" int ance_merge_topk_host(const float* const* D, const int64_t* const*
   for (auto& t : th) t.join();
   return ANCE_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// ann_training_data_N writer — replaces the per-query Python formatting of drivers/run_ann_data_gen.py:318-329:
+//   f.write("{}\t{}\t{}\n".format(query_id, pos_pid, ','.join(str(neg_pid) for neg_pid in ...)))
+// Lines are emitted in `order` (the shuffled query order); a query without negatives (count 0) still gets its line with an
+// empty list, as the reference's join of an empty list does.
+// ------------------------------------------------------------------------------------------------
+#include <stdio.h>
+
+#include <charconv>
+#include <string>
+
+extern "C" int ance_write_training_data_host(const char* path, const int64_t* qids, const int64_t* pos, const int64_t* neg,
+                                             const int64_t* counts, const int64_t* order, int64_t n, int neg_stride,
+                                             int64_t* lines_written) {
+  ANCE_REQUIRE(path && (n == 0 || (qids && pos && neg && counts && order)) && n >= 0 && neg_stride >= 0,
+               "ance_write_training_data_host: bad arguments");
+  FILE* f = fopen(path, "wb");
+  ANCE_REQUIRE(f != nullptr, "ance_write_training_data_host: cannot open %s", path);
+  std::string buf;
+  buf.reserve(1 << 20);
+  char tmp[24];
+  auto put = [&](int64_t v) {
+    auto r = std::to_chars(tmp, tmp + sizeof(tmp), v);
+    buf.append(tmp, r.ptr);
+  };
+  int64_t written = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t q = order[i];
+    if (q < 0 || q >= n || counts[q] < 0 || counts[q] > neg_stride) {
+      fclose(f);
+      ance::set_error("ance_write_training_data_host: order / counts out of range at line %lld", (long long)i);
+      return ANCE_ERR_INVALID;
+    }
+    put(qids[q]);
+    buf.push_back('\t');
+    put(pos[q]);
+    buf.push_back('\t');
+    for (int64_t c = 0; c < counts[q]; ++c) {
+      if (c) buf.push_back(',');
+      put(neg[q * neg_stride + c]);
+    }
+    buf.push_back('\n');
+    ++written;
+    if (buf.size() > (1 << 20) - 8192) {
+      if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); ance::set_error("ance_write_training_data_host: write failed"); return ANCE_ERR_INVALID; }
+      buf.clear();
+    }
+  }
+  const bool ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+  if (fclose(f) != 0 || !ok) { ance::set_error("ance_write_training_data_host: write failed"); return ANCE_ERR_INVALID; }
+  if (lines_written) *lines_written = written;
+  return ANCE_OK;
+}

@@ -340,10 +340,12 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
 
     for bi, b0 in enumerate(range(0, nq, QB)):
         nb = min(QB, nq - b0)
-        qb = queries_all[b0:b0 + nb]
-        if nb < QB and W > 1:      # ragged last block: pad so that every rank owns the same number of rows
-            qb = torch.cat([qb, qb.new_zeros((QB - nb, qb.shape[1]))], dim=0)
-        D, I = local_search(qb.contiguous(), k, offset)
+        D, I = local_search(queries_all[b0:b0 + nb].contiguous(), k, offset)
+        if nb < QB and W > 1:
+            # ragged last block: pad the RESULTS (not the queries: an all-zero query ties with every row, which no
+            # certificate can resolve, and would be sent to the brute force) so that the all-to-all splits are equal
+            D = torch.cat([D, D.new_full((QB - nb, k), torch.finfo(torch.float32).min)], dim=0)
+            I = torch.cat([I, I.new_full((QB - nb, k), -1)], dim=0)
         st = stage[bi % 2]
         if st.job is not None:
             st.job.result()        # the staging buffers are free again
@@ -473,17 +475,22 @@ def generate_new_ann(args, output_num, checkpoint_path, training_query_positive_
     print("Rank:" + str(getattr(args, "rank", 0)) + " --- ANN NDCG@10:" + str(dev_ndcg))
     t = lap("post_ndcg_s", t)
     sampler = "reference" if args.reference_sampling else "fast"
+    arrays = sampler == "fast"        # array form + native line writer; the reference sampler keeps the dict / Python path
     negatives, mrr, nq = postprocess.generate_negatives(
         query_embedding2id, passage_embedding2id, training_query_positive_id, I, args.negative_sample,
-        select_topk=args.ann_measure_topk_mrr, sampler=sampler, seed=args.seed)
+        select_topk=args.ann_measure_topk_mrr, sampler=sampler, seed=args.seed, as_arrays=arrays)
     if args.ann_measure_topk_mrr:
         print("Rank:" + str(getattr(args, "rank", 0)) + " --- ANN MRR:" + str(mrr / max(nq, 1)))
     t = lap("post_negatives_s", t)
     logger.info("***** Construct ANN Triplet *****")
     os.makedirs(args.output_dir, exist_ok=True)
-    postprocess.write_training_data(os.path.join(args.output_dir, "ann_training_data_" + str(output_num)),
-                                    query_embedding2id, training_query_positive_id, negatives, sampler=sampler,
-                                    seed=args.seed)
+    data_path = os.path.join(args.output_dir, "ann_training_data_" + str(output_num))
+    if arrays:
+        postprocess.write_training_data_arrays(data_path, query_embedding2id, training_query_positive_id, negatives[0],
+                                               negatives[1], seed=args.seed)
+    else:
+        postprocess.write_training_data(data_path, query_embedding2id, training_query_positive_id, negatives,
+                                        sampler=sampler, seed=args.seed)
     postprocess.write_ndcg(os.path.join(args.output_dir, "ann_ndcg_" + str(output_num)), dev_ndcg, checkpoint_path)
     lap("post_write_s", t)
     args.last_refresh_timing = {"encode_s": t_enc - t_start, "search_s": t_search - t_enc, "post_s": time.time() - t_search,
@@ -562,10 +569,30 @@ def set_env(args):
         args.n_gpu = 1
         args.world_size = dist.get_world_size()
     args.rank = _world()[1]
+    _warm_collectives(args.device)
     logging.basicConfig(format="%(asctime)s - %(levelname)s - %(name)s -   %(message)s", datefmt="%m/%d/%Y %H:%M:%S",
                         level=logging.INFO if args.local_rank in [-1, 0] else logging.WARN)
     if args.seed is not None:
         random.seed(args.seed)
+
+
+def _warm_collectives(device) -> None:
+    """Process start-up, like the reference's DDP wrap (run_ann_data_gen.py:128-135): the first all-gather / all-to-all
+    on an NCCL communicator sets up its rings and the peer-to-peer channels of every pair of ranks (seconds on 8 GPUs).
+    Done once here so that it is not billed to the first refresh's search."""
+    W, _ = _world()
+    if W == 1:
+        return
+    x = torch.zeros((W, 8), dtype=torch.float32, device=device)
+    y = torch.empty((W * W, 8), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(y, x)
+    z = torch.empty_like(x)
+    dist.all_to_all_single(z, x)
+    zi = torch.empty((W, 8), dtype=torch.int64, device=device)
+    dist.all_to_all_single(zi, torch.zeros_like(zi))
+    dist.gather(x, [torch.empty_like(x) for _ in range(W)] if _world()[1] == 0 else None, dst=0)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
 
 
 def ann_data_gen(args, backend=None):

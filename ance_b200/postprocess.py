@@ -41,14 +41,16 @@ def _first_occurrence(pids: np.ndarray) -> np.ndarray:
 
 def generate_negatives(query_embedding2id: np.ndarray, passage_embedding2id: np.ndarray, positives: Dict[int, int],
                        I: np.ndarray, negative_sample: int, select_topk: bool = False, sampler: str = "fast",
-                       seed: Optional[int] = None) -> Tuple[Dict[int, List[int]], float, int]:
+                       seed: Optional[int] = None, as_arrays: bool = False, threads: int = 8):
     """-> ({qid: [neg pids]}, mrr_sum, num_queries).  `I` holds global passage ROWS (faiss labels);
     every query of `query_embedding2id` is effective (the reference builds effective_q_id from the same
-    array, run_ann_data_gen.py:305)."""
+    array, run_ann_data_gen.py:305).
+    as_arrays: -> ((neg [nq, negative_sample] int64 padded with -1, counts [nq]), mrr_sum, num_queries) instead of the
+    dict — what `write_training_data_arrays` consumes without creating nq Python lists."""
     nq, k = I.shape
     qids = np.asarray(query_embedding2id).reshape(-1).astype(np.int64)
     if nq == 0:
-        return {}, 0.0, 0
+        return ((np.empty((0, negative_sample), np.int64), np.empty(0, np.int64)) if as_arrays else {}), 0.0, 0
     pos = np.fromiter((positives[int(q)] for q in qids), dtype=np.int64, count=nq)  # KeyError like the reference
     p2id = np.asarray(passage_embedding2id).reshape(-1)
     if select_topk:
@@ -65,14 +67,20 @@ def generate_negatives(query_embedding2id: np.ndarray, passage_embedding2id: np.
         # Only the head of the shuffled list is ever read (the loop stops after negative_sample valid candidates), so
         # draw the first m positions of a uniform random permutation -- the m smallest of k i.i.d. keys, in key order --
         # instead of shuffling all k; rows that run out of valid candidates within m fall back to a full permutation.
-        rng = np.random.default_rng(seed)
+        # Row blocks are independent (their own generator, seeded by (seed, block)): they run on a few threads, numpy
+        # releases the GIL inside random / argpartition / sort / take.
         m = min(k, max(negative_sample + 16, 32))
-        out: Dict[int, List[int]] = {}
-        mrr = 0.0
-        for lo in range(0, nq, _FAST_CHUNK):   # row blocks: the temporaries stay cache-sized and are reused
+        mat = np.full((nq, negative_sample), -1, dtype=np.int64)
+        counts = np.zeros(nq, dtype=np.int64)
+        blocks = list(range(0, nq, _FAST_CHUNK))
+        entropy = np.random.SeedSequence().entropy if seed is None else seed
+
+        def work(bi: int) -> float:
+            lo = blocks[bi]
             hi = min(nq, lo + _FAST_CHUNK)
+            rng = np.random.default_rng([entropy, bi]) if len(blocks) > 1 else np.random.default_rng(seed if seed is not None else entropy)
             keys = rng.random((hi - lo, k), dtype=np.float32)
-            Ic, qc, pc = I[lo:hi], qids[lo:hi], pos[lo:hi]
+            Ic, pc = I[lo:hi], pos[lo:hi]
             if m < k:
                 part = np.argpartition(keys, m - 1, axis=1)[:, :m]
                 head = np.take_along_axis(part, np.argsort(np.take_along_axis(keys, part, axis=1), axis=1), axis=1)
@@ -84,31 +92,50 @@ def generate_negatives(query_embedding2id: np.ndarray, passage_embedding2id: np.
                 pids_h = p2id[np.where(sel < 0, 0, sel)]
                 # (<=: the reference's break needs one more valid candidate than it keeps)
                 short = ((_first_occurrence(pids_h) & (pids_h != pc[:, None])).sum(axis=1) <= negative_sample) | (sel < 0).any(axis=1)
+            mrr = 0.0
             if short.any():
                 rows = np.nonzero(short)[0]
                 full = np.argsort(keys[rows], axis=1)
-                o2, m2, _ = _negatives_from_selection(qc[rows], pc[rows], p2id, np.take_along_axis(Ic[rows], full, axis=1), negative_sample)
-                keep = ~short
-                o1, m1, _ = _negatives_from_selection(qc[keep], pc[keep], p2id, sel[keep], negative_sample)
-                o1.update(o2)
-                out.update((int(q), o1[int(q)]) for q in qc)
-                mrr += m1 + m2
+                m2, c2, r2 = _negatives_arrays(pc[rows], p2id, np.take_along_axis(Ic[rows], full, axis=1), negative_sample)
+                mat[lo + rows], counts[lo + rows] = m2, c2
+                keep = np.nonzero(~short)[0]
+                m1, c1, r1 = _negatives_arrays(pc[keep], p2id, sel[keep], negative_sample)
+                mat[lo + keep], counts[lo + keep] = m1, c1
+                mrr = r1 + r2
             else:
-                o1, m1, _ = _negatives_from_selection(qc, pc, p2id, sel, negative_sample)
-                out.update(o1)
-                mrr += m1
-        return out, mrr, nq
+                mat[lo:hi], counts[lo:hi], mrr = _negatives_arrays(pc, p2id, sel, negative_sample)
+            return mrr
+
+        if len(blocks) > 1 and threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(threads, len(blocks))) as ex:
+                mrr = float(sum(ex.map(work, range(len(blocks)))))
+        else:
+            mrr = float(sum(work(bi) for bi in range(len(blocks))))
+        if as_arrays:
+            return (mat, counts), mrr, nq
+        return _dict_from_arrays(qids, mat, counts), mrr, nq
     else:
         raise ValueError(f"unknown sampler {sampler!r}")
-    return _negatives_from_selection(qids, pos, p2id, sel, negative_sample)
+    mat, counts, mrr = _negatives_arrays(pos, p2id, sel, negative_sample)
+    if as_arrays:
+        return (mat, counts), mrr, nq
+    return _dict_from_arrays(qids, mat, counts), mrr, nq
 
 
-def _negatives_from_selection(qids: np.ndarray, pos: np.ndarray, p2id: np.ndarray, sel: np.ndarray,
-                              negative_sample: int) -> Tuple[Dict[int, List[int]], float, int]:
-    """The reference's scan (run_ann_data_gen.py:357-385) over the candidate rows `sel` [nq, m] in the given order."""
+def _dict_from_arrays(qids: np.ndarray, mat: np.ndarray, counts: np.ndarray) -> Dict[int, List[int]]:
+    if mat.shape[0] and (counts == mat.shape[1]).all():   # the common case: one conversion instead of nq slices
+        return dict(zip(qids.tolist(), mat.tolist()))
+    return {int(q): mat[r, :counts[r]].tolist() for r, q in enumerate(qids.tolist())}
+
+
+def _negatives_arrays(pos: np.ndarray, p2id: np.ndarray, sel: np.ndarray, negative_sample: int):
+    """The reference's scan (run_ann_data_gen.py:357-385) over the candidate rows `sel` [nq, m] in the given order.
+    -> (neg pids [nq, negative_sample] padded with -1, counts [nq], mrr_sum)."""
     nq = sel.shape[0]
+    mat = np.full((nq, negative_sample), -1, dtype=np.int64)
     if nq == 0:
-        return {}, 0.0, 0
+        return mat, np.zeros(0, dtype=np.int64), 0.0
     if (sel < 0).any():
         raise IndexError("search returned -1 labels (fewer rows than k); the reference would index "
                          "passage_embedding2id[-1] silently — refusing")
@@ -125,15 +152,15 @@ def _negatives_from_selection(qids: np.ndarray, pos: np.ndarray, p2id: np.ndarra
     hit = is_pos & (ranks <= 10) & (np.arange(m)[None, :] < brk[:, None])
     mrr = float((hit / ranks).sum())
     counts = take.sum(axis=1)
-    flat = pids[take]
-    if (counts == negative_sample).all():   # the common case: one reshape instead of nq boolean gathers
-        rows = flat.reshape(nq, negative_sample).tolist()
-        return dict(zip(qids.tolist(), rows)), mrr, nq
-    out: Dict[int, List[int]] = {}
-    ends = np.cumsum(counts)
-    for r in range(nq):
-        out[int(qids[r])] = flat[ends[r] - counts[r]:ends[r]].tolist()
-    return out, mrr, nq
+    r_idx, c_idx = np.nonzero(take)
+    mat[r_idx, csum[r_idx, c_idx] - 1] = pids[r_idx, c_idx]
+    return mat, counts.astype(np.int64), mrr
+
+
+def _negatives_from_selection(qids: np.ndarray, pos: np.ndarray, p2id: np.ndarray, sel: np.ndarray,
+                              negative_sample: int) -> Tuple[Dict[int, List[int]], float, int]:
+    mat, counts, mrr = _negatives_arrays(pos, p2id, sel, negative_sample)
+    return _dict_from_arrays(np.asarray(qids), mat, counts), mrr, sel.shape[0]
 
 
 def ndcg_cut(ranked_pids: Sequence[int], qrel: Dict[int, int], cut: int = 10) -> float:
@@ -195,6 +222,27 @@ def write_training_data(path: str, query_embedding2id: np.ndarray, positives: Di
             n += 1
     os.replace(tmp, path)  # a reader never sees a partial file (the reference writes in place)
     return n
+
+
+def write_training_data_arrays(path: str, query_embedding2id: np.ndarray, positives: Dict[int, int], neg: np.ndarray,
+                               counts: np.ndarray, seed: Optional[int] = None) -> int:
+    """write_training_data for the array form of the negatives (generate_negatives(as_arrays=True)): the same lines in
+    the same ("fast" sampler) order, formatted and written by libance_b200's host code instead of nq Python joins."""
+    import ctypes as C
+    from . import _lib
+    qids = np.ascontiguousarray(np.asarray(query_embedding2id).reshape(-1), dtype=np.int64)
+    n = len(qids)
+    pos = np.fromiter((positives[int(q)] for q in qids), dtype=np.int64, count=n)
+    order = np.ascontiguousarray(np.random.default_rng(None if seed is None else seed + 1).permutation(n), dtype=np.int64)
+    neg = np.ascontiguousarray(neg, dtype=np.int64)
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    tmp = staging_path(path)
+    written = C.c_int64()
+    _lib.check(_lib.load().ance_write_training_data_host(tmp.encode(), qids.ctypes.data, pos.ctypes.data, neg.ctypes.data,
+                                                         counts.ctypes.data, order.ctypes.data, n, neg.shape[1],
+                                                         C.byref(written)))
+    os.replace(tmp, path)
+    return int(written.value)
 
 
 def write_ndcg(path: str, ndcg: float, checkpoint: str) -> None:

@@ -97,6 +97,12 @@ int ance_index_set_param(ance_index_t idx, const char* name, double value);
 int ance_merge_topk_host(const float* const* D, const int64_t* const* I, int n_shards, int64_t nq, int k,
                          float* D_out, int64_t* I_out, int n_threads);
 
+/* ann_training_data_N writer (host only) — replaces the per-query formatting loop of drivers/run_ann_data_gen.py:318-329.
+ * Line i = "qid \t pos \t n1,n2,...\n" of query order[i]; neg [n, neg_stride] holds counts[q] valid ids per row. */
+int ance_write_training_data_host(const char* path, const int64_t* qids, const int64_t* pos, const int64_t* neg,
+                                  const int64_t* counts, const int64_t* order, int64_t n, int neg_stride,
+                                  int64_t* lines_written);
+
 /* ------------------------------------------------------------------------------------------------
  * Dual-encoder forward — replaces the HF RobertaModel/BertModel forward + embeddingHead + norm
  *   reference: model/models.py:149-157 (RobertaDot_NLL_LN.query_emb/body_emb),

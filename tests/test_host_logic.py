@@ -338,3 +338,32 @@ def test_postprocess_equals_oracle_property():
         assert got[0] == want[0] and got[2] == want[2] and got[1] == pytest.approx(want[1], abs=1e-12)
 
     run()
+
+
+def test_array_negatives_and_native_writer_equal_the_python_path(tmp_path):
+    """generate_negatives(as_arrays=True) + write_training_data_arrays (threaded row blocks, libance_b200's host writer)
+    against the dict / Python-join path: same negatives, same bytes — including rows with fewer than `negative_sample`
+    candidates and several row blocks."""
+    from ance_b200 import postprocess
+    rng = np.random.default_rng(12)
+    nq, k, n_rows, ns = 700, 60, 4000, 9
+    I = np.stack([rng.permutation(n_rows)[:k] for _ in range(nq)]).astype(np.int64)
+    q2id = rng.permutation(5000)[:nq].astype(np.int64)
+    p2id = np.arange(n_rows, dtype=np.int64)
+    p2id[:3900] = np.arange(3900) % 7                     # most rows share 7 pids: many queries have < 9 distinct candidates
+    pos = {int(q): int(p2id[I[r, 5]]) for r, q in enumerate(q2id)}
+    old_chunk = postprocess._FAST_CHUNK
+    postprocess._FAST_CHUNK = 128                          # several blocks -> the threaded path
+    try:
+        for select_topk in (False, True):
+            d, mrr_d, _ = postprocess.generate_negatives(q2id, p2id, pos, I, ns, select_topk=select_topk, sampler="fast", seed=4)
+            (mat, cnt), mrr_a, _ = postprocess.generate_negatives(q2id, p2id, pos, I, ns, select_topk=select_topk, sampler="fast",
+                                                                  seed=4, as_arrays=True)
+            assert mrr_d == mrr_a and (cnt <= ns).all() and (cnt < ns).any()
+            assert d == {int(q): mat[r, :cnt[r]].tolist() for r, q in enumerate(q2id)}
+            a, b = str(tmp_path / f"py{select_topk}"), str(tmp_path / f"native{select_topk}")
+            n1 = postprocess.write_training_data(a, q2id, pos, d, sampler="fast", seed=4)
+            n2 = postprocess.write_training_data_arrays(b, q2id, pos, mat, cnt, seed=4)
+            assert n1 == n2 == nq and open(a, "rb").read() == open(b, "rb").read()
+    finally:
+        postprocess._FAST_CHUNK = old_chunk
