@@ -261,8 +261,10 @@ def all_gather_ids(ids: np.ndarray, device) -> np.ndarray:
     return all_gather_rows(t[:, None])[:, 0].cpu().numpy()
 
 
-#: queries per search block: 74 CTA pairs x 256 query rows = one full wave of the coarse kernel on a B200
-QUERY_BLOCK = 18944
+#: queries per search block: four full waves of the coarse kernel on a B200 (74 CTA pairs x 256 query rows each).  One wave
+#: per block (18,944) left ~28 ms of per-call latency (stream sync for the tier counters, all-to-all, staging) for every
+#: 32 ms of kernels when the corpus is spread over 8 GPUs; the merge of a block still overlaps the next block's search.
+QUERY_BLOCK = 75776
 
 
 class _Staging:
