@@ -345,65 +345,96 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         } else {
           const int stb = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
           all_skip = stb == 0;   // a fully masked block of a row that has real keys: contributes nothing
-          // pass 1: row max (of the raw scores when `plain`: scale > 0 commutes with max)
-          float m_blk = -INFINITY;
-          if (!all_skip) {
+          // p = exp2(t - m_ref) for the whole block: row sum, 16-bit P into swizzled smem; returns max(t - m_ref)
+          auto exp_pass = [&](float m_ref, float& rs_out) -> float {
+            float rs_ = 0.f, mu = -INFINITY;
+            const float nm = -m_ref;
 #pragma unroll 1
             for (int c = 0; c < kTile; c += 32) {
               const int sc_ = (stb >> (c >> 4)) & 3;
-              if (sc_ == 0) continue;
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(tmem_S + lane_sel + c, v);
-              tmem_ld_wait();
-              if (plain) {
+              uint32_t pk[16];
+              if (sc_ == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
-              } else if (sc_ == 1) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]) * p.scale_log2);
+                for (int i = 0; i < 16; ++i) pk[i] = 0u;
               } else {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_S + lane_sel + c, v);
+                tmem_ld_wait();
+                if (sc_ == 1) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[c + i]));
+                  for (int i = 0; i < 32; i += 2) {
+                    const float u0 = fmaf(__uint_as_float(v[i]), p.scale_log2, nm);
+                    const float u1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, nm);
+                    mu = fmaxf(mu, fmaxf(u0, u1));
+                    const float p0 = ex2_ftz(u0), p1 = ex2_ftz(u1);
+                    rs_ += p0 + p1;
+                    pk[i >> 1] = act16::Act<FMT>::pack2(p0, p1);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; i += 2) {
+                    const float u0 = fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[c + i]) + nm;
+                    const float u1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, sbias[c + i + 1]) + nm;
+                    mu = fmaxf(mu, fmaxf(u0, u1));
+                    const float p0 = ex2_ftz(u0), p1 = ex2_ftz(u1);
+                    rs_ += p0 + p1;
+                    pk[i >> 1] = act16::Act<FMT>::pack2(p0, p1);
+                  }
+                }
               }
+              store_chunks(sP + (c >> 6) * (kTile * 128) + row * 128, (c & 63) >> 3, pk);
             }
-          }
-          if (plain) m_blk *= p.scale_log2;
-          m_new = fmaxf(m_run, m_blk);
-          alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
-          // pass 2: p = exp2(t - m_new), row sum, 16-bit P into swizzled smem
-          rsum = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < kTile; c += 32) {
-            const int sc_ = (stb >> (c >> 4)) & 3;
-            uint32_t pk[16];
-            if (sc_ == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            rs_out = rs_;
+            return mu;
+          };
+          // Blocks after the first: ONE trip over the scores, relative to the running maximum (the block's own maximum is
+          // tracked on the way).  exp2(t - m_run) stays <= 2^8 unless a score exceeds every earlier one by more than 8
+          // (log2 units) — then, and only then, the warp redoes the block relative to the true maximum.  The softmax is
+          // the same function either way (numerator and denominator carry the same factor 2^(m_true - m_ref)).
+          const bool optimistic = __all_sync(0xffffffffu, j > 0 && m_run > kRealMax);
+          if (optimistic) {
+            m_new = m_run;
+            alpha = 1.f;
+            rsum = 0.f;
+            if (!all_skip) {
+              const float over = exp_pass(m_run, rsum);
+              if (__any_sync(0xffffffffu, over > 8.0f)) {
+                m_new = fmaxf(m_run, m_run + over);
+                alpha = exp2f(m_run - m_new);
+                exp_pass(m_new, rsum);
+              }
             } else {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(tmem_S + lane_sel + c, v);
-              tmem_ld_wait();
-              const float nm = -m_new;
-              if (sc_ == 1) {
+              float dummy;
+              exp_pass(m_run, dummy);   // (writes the zero P tile; no TMEM reads: every chunk state is 0)
+            }
+          } else {
+            // first block of an item (or no real key seen yet): pass 1 = row max (of the raw scores when `plain`:
+            // scale > 0 commutes with max), pass 2 = exp relative to it
+            float m_blk = -INFINITY;
+            if (!all_skip) {
+#pragma unroll 1
+              for (int c = 0; c < kTile; c += 32) {
+                const int sc_ = (stb >> (c >> 4)) & 3;
+                if (sc_ == 0) continue;
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_S + lane_sel + c, v);
+                tmem_ld_wait();
+                if (plain) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                  const float p0 = ex2_ftz(fmaf(__uint_as_float(v[i]), p.scale_log2, nm));
-                  const float p1 = ex2_ftz(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, nm));
-                  rsum += p0 + p1;
-                  pk[i >> 1] = act16::Act<FMT>::pack2(p0, p1);
-                }
-              } else {
+                  for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+                } else if (sc_ == 1) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                  const float t0 = fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[c + i]);
-                  const float t1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, sbias[c + i + 1]);
-                  const float p0 = ex2_ftz(t0 + nm), p1 = ex2_ftz(t1 + nm);
-                  rsum += p0 + p1;
-                  pk[i >> 1] = act16::Act<FMT>::pack2(p0, p1);
+                  for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]) * p.scale_log2);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, fmaf(__uint_as_float(v[i]), p.scale_log2, sbias[c + i]));
                 }
               }
             }
-            store_chunks(sP + (c >> 6) * (kTile * 128) + row * 128, (c & 63) >> 3, pk);
+            if (plain) m_blk *= p.scale_log2;
+            m_new = fmaxf(m_run, m_blk);
+            alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+            exp_pass(m_new, rsum);
           }
         }
         fence_proxy_async_smem();
