@@ -178,6 +178,34 @@ def test_inference_dumps(tmp_path):
     assert not (out / "ann_training_data_0").exists()
 
 
+def test_offline_evaluation_of_inference_dumps(tmp_path):
+    """SURVEY.md 8(f) row 4, second half: the dumps of `--inference` -> ance_b200.evaluation (cells 9-13 of the reference's
+    notebook): the GPU full-rank search must equal the oracle's on the dumped embeddings, the metrics must equal the
+    notebook loop restated in tests/test_evaluation.py, and a rerank over first-stage candidates that contain the positive
+    must find it."""
+    from ance_b200 import evaluation as ev
+    from ance_b200.drivers import run_ann_data_gen as drv
+    from tests.test_evaluation import _notebook_eval
+    data, ckpt, caches, train_pos, dev_pos, *_ = _make_world(tmp_path, n_p=1200, n_q=20, n_dev=40)
+    out = tmp_path / "ann"
+    drv.main(_argv(data, ckpt, out, tmp_path, extra=("--inference",)))
+    q, q2id = ev.load_dumps(str(out), "dev_query_0_")
+    p, p2id = ev.load_dumps(str(out), "passage_0_")
+    assert q.shape == (40, 768) and p.shape == (1200, 768)
+    I = ev.full_rank(q, p, 100)
+    _, Io = flat_ip_oracle.search(np.ascontiguousarray(p), np.ascontiguousarray(q), 100)
+    assert (I == Io).all()
+    rng = np.random.default_rng(2)
+    first = {int(qid): [int(x) for x in rng.permutation(1200)[:50]] + list(dev_pos[int(qid)]) for qid in q2id}
+    res = ev.evaluate_dumps(str(out), 0, dev_pos, topN=100, first_stage=first)
+    want = _notebook_eval(q2id, p2id, dev_pos, I, 100)
+    for k, v in want.items():
+        assert res["full_rank"][k] == pytest.approx(v, abs=1e-12), k
+    rr = res["rerank"]
+    assert rr["recall@100"] == 1.0 and rr["eval_query_cnt"] == 40 and 0.0 < rr["mrr"] <= 1.0   # the positive is a candidate
+    assert set(res["full_rank"]) == set(rr)
+
+
 def test_no_cuda_flag_is_refused(tmp_path):
     from ance_b200.drivers import run_ann_data_gen as drv
     args = drv.get_arguments(["--data_dir", "d", "--training_dir", "t", "--init_model_dir", "i", "--model_type",
