@@ -100,7 +100,7 @@ def test_refresh_end_to_end(tmp_path):
     ref = orc.body_emb(torch.from_numpy(ids[:64]), torch.from_numpy(np.arange(128)[None, :] < lens[:64, None]))
     cos = torch.nn.functional.cosine_similarity(torch.from_numpy(P[:64]), ref, dim=-1).min().item()
     assert cos >= 0.9995
-    # retrieval overlap@20 between GPU-encoded and oracle-encoded corpora on the oracle search
+    # (the retrieval-overlap gate against the fp32-encoded corpus: tests/test_gpu_encoder.py::test_retrieval_overlap_at_200)
     # resume bookkeeping: the next run starts at output 1 and, with no new checkpoint, only sleeps
     assert drv.get_latest_ann_data(str(out))[0] == 0
 
