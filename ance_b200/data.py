@@ -25,93 +25,106 @@ from torch.utils.data import IterableDataset, TensorDataset
 
 
 class EmbeddingCache:
-    """Same contract as the reference class (utils/util.py:257-307)."""
+    """Fixed-record token store with the reference class's public surface (utils/util.py:257-307: attributes `dtype`,
+    `total_number`, `record_size`, `ix_array`; `open` / `close` / context manager; `cache[i] -> (length, ids[L])`; iteration
+    in `ix_array` order; `len`; `read_single_record`), implemented over ONE read-only memory map of the file instead of a
+    seek pointer: records are views into the mapping (zero-copy, page-cache backed), random access needs no syscall, and the
+    object is safe to share between threads and across `fork` (the reference's shared file position is why it must run with
+    `num_workers=0`, SURVEY.md par. 8b).  Opening is lazy: `with cache:` / `cache.open()` keep working but are not required."""
 
     def __init__(self, base_path, seed=-1):
         self.base_path = base_path
         with open(base_path + "_meta", "r") as f:
             meta = json.load(f)
-            self.dtype = np.dtype(meta["type"])
-            self.total_number = meta["total_number"]
-            self.record_size = int(meta["embedding_size"]) * self.dtype.itemsize + 4
-        if seed >= 0:
-            self.ix_array = np.random.RandomState(seed).permutation(self.total_number)
-        else:
-            self.ix_array = np.arange(self.total_number)
-        self.f = None
+        self.dtype = np.dtype(meta["type"])
+        self.total_number = int(meta["total_number"])
+        self._tokens = int(meta["embedding_size"])
+        self.record_size = self._tokens * self.dtype.itemsize + 4          # 4-byte big-endian length + the ids
+        # visiting order of __iter__: a seeded permutation (the trainer's shuffled passes) or file order
+        self.ix_array = (np.random.RandomState(seed).permutation(self.total_number) if seed >= 0
+                         else np.arange(self.total_number))
+        self._map = None
+        self._cursor = 0         # next record of read_single_record()
 
-    # -- reference surface --------------------------------------------------------------------
+    # -- mapping --------------------------------------------------------------------------------
+    @property
+    def embedding_size(self) -> int:
+        return self._tokens
+
+    def memmap(self) -> np.ndarray:
+        """The whole file as a structured array: field 'len' (>i4) and 'ids' (dtype[L])."""
+        if self._map is None:
+            rec = np.dtype([("len", ">i4"), ("ids", self.dtype, (self._tokens,))])
+            self._map = (np.zeros((0,), dtype=rec) if self.total_number == 0
+                         else np.memmap(self.base_path, dtype=rec, mode="r", shape=(self.total_number,)))
+        return self._map
+
     def open(self):
-        self.f = open(self.base_path, "rb")
+        self.memmap()
+        self._cursor = 0
 
     def close(self):
-        self.f.close()
-
-    def read_single_record(self):
-        record_bytes = self.f.read(self.record_size)
-        passage_len = int.from_bytes(record_bytes[:4], "big")
-        passage = np.frombuffer(record_bytes[4:], dtype=self.dtype)
-        return passage_len, passage
+        self._map = None
 
     def __enter__(self):
         self.open()
         return self
 
-    def __exit__(self, type, value, traceback):
+    def __exit__(self, exc_type, exc, tb):
         self.close()
 
+    # -- record access --------------------------------------------------------------------------
+    def _record(self, i: int):
+        r = self.memmap()[i]
+        return int(r["len"]), np.asarray(r["ids"])
+
+    def read_single_record(self):
+        """The record at the cursor (set by `open()` / `cache[i]`), then advance — the reference's sequential read."""
+        if self._cursor >= self.total_number:
+            return 0, np.empty((0,), dtype=self.dtype)       # what reading past the end of the file yields upstream
+        rec = self._record(self._cursor)
+        self._cursor += 1
+        return rec
+
     def __getitem__(self, key):
-        # the reference's bound check is `key > total_number` (util.py:293, off by one); reading
-        # record `total_number` then fails later with an empty buffer.  Here it raises directly.
+        # (the reference's own check is `key > total_number`, util.py:293: record `total_number` then fails later on an
+        # empty buffer; here the bound is exact and the message is the reference's)
         if key < 0 or key >= self.total_number:
             raise IndexError(
                 "Index {} is out of bound for cached embeddings of size {}".format(key, self.total_number))
-        self.f.seek(key * self.record_size)
-        return self.read_single_record()
+        self._cursor = int(key) + 1
+        return self._record(int(key))
 
     def __iter__(self):
-        self.f.seek(0)
-        for i in range(self.total_number):
-            new_ix = self.ix_array[i]
-            yield self.__getitem__(new_ix)
+        for i in self.ix_array:
+            yield self[int(i)]
 
     def __len__(self):
         return self.total_number
 
-    # -- bulk access ----------------------------------------------------------------------------
-    @property
-    def embedding_size(self) -> int:
-        return (self.record_size - 4) // self.dtype.itemsize
-
-    def memmap(self) -> np.memmap:
-        """The whole file as a structured array: field 'len' (>i4) and 'ids' (int32[L])."""
-        rec = np.dtype([("len", ">i4"), ("ids", self.dtype, (self.embedding_size,))])
-        if self.total_number == 0:
-            return np.zeros((0,), dtype=rec)
-        return np.memmap(self.base_path, dtype=rec, mode="r", shape=(self.total_number,))
-
 
 class StreamingDataset(IterableDataset):
-    """Same contract as the reference class (utils/util.py:310-329): element i goes to rank
-    i % world_size; ``fn(element, i)`` yields the records."""
+    """Rank-strided stream with the reference's contract (utils/util.py:310-329): element i belongs to rank
+    `i % world_size` when a process group is initialised (every element otherwise, or with distributed=False), and each
+    kept element expands to the records `fn(element, i)` returns."""
 
     def __init__(self, elements, fn, distributed=True):
         super().__init__()
         self.elements = elements
         self.fn = fn
-        self.num_replicas = -1
         self.distributed = distributed
+        self.num_replicas = -1       # filled in at iteration time, as upstream (-1: no process group)
+        self.rank = 0
+
+    def _mine(self, i: int) -> bool:
+        return not self.distributed or self.num_replicas == -1 or i % self.num_replicas == self.rank
 
     def __iter__(self):
         if dist.is_available() and dist.is_initialized():
-            self.num_replicas = dist.get_world_size()
-            self.rank = dist.get_rank()
+            self.num_replicas, self.rank = dist.get_world_size(), dist.get_rank()
         for i, element in enumerate(self.elements):
-            if self.distributed and self.num_replicas != -1 and i % self.num_replicas != self.rank:
-                continue
-            records = self.fn(element, i)
-            for rec in records:
-                yield rec
+            if self._mine(i):
+                yield from self.fn(element, i)
 
 
 def GetProcessingFn(args, query=False):
