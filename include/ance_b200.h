@@ -165,7 +165,7 @@ int ance_encoder_forward_varlen(ance_encoder_t enc, const int32_t* ids_dev, cons
                                 const int32_t* lens_host, int B, int L, float* out_dev, void* stream);
 /* Tunables: "prune_last_layer" (default 1): in the last layer only token 0 of every sequence is read
  * downstream, so out-projection / FFN / LayerNorm run on those rows only (result-identical; bench.py reports
- * the executed FLOPs beside the algorithmic ones).  "ln_rows_per_warp" (1, 2 or 4; default 2, process-wide): rows a warp
+ * the executed FLOPs beside the algorithmic ones).  "ln_rows_per_warp" (1, 2, 4, or 3 = two rows held packed; default 2, process-wide): rows a warp
  * of the LayerNorm kernel normalises side by side (bit-identical results; 2 is the fastest on B200).  "varlen_align" (1 | 16):
  * see ance_encoder_forward_varlen. */
 int ance_encoder_set_param(ance_encoder_t enc, const char* name, double value);
