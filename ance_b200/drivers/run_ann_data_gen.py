@@ -273,6 +273,7 @@ class _Staging:
     def __init__(self, rows: int, k: int, with_scores: bool, pin: bool):
         self.D = torch.empty((rows, k), dtype=torch.float32, pin_memory=pin) if with_scores else None
         self.I = torch.empty((rows, k), dtype=torch.int64, pin_memory=pin)
+        self.merged = None      # (D, I) numpy scratch of the merge of this slot's block, reused across blocks
         self.job = None
 
 
@@ -335,9 +336,11 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
             own_I.append(st.I[:n_valid].numpy().copy())
         else:
             Dv, Iv = st.D.numpy().reshape(W, part, k), st.I.numpy().reshape(W, part, k)
+            if st.merged is None or st.merged[0].shape[0] < n_valid:
+                st.merged = (np.empty((part, k), dtype=np.float32), np.empty((part, k), dtype=np.int64))
             _, Im = merge_topk_host([Dv[s, :n_valid] for s in range(W)], [Iv[s, :n_valid] for s in range(W)], k,
-                                    merge_threads)
-            own_I.append(Im)
+                                    merge_threads, out=(st.merged[0][:n_valid], st.merged[1][:n_valid]))
+            own_I.append(Im.copy())
         own_q.append(np.arange(q0, q0 + n_valid, dtype=np.int64))
 
     for bi, b0 in enumerate(range(0, nq, QB)):

@@ -176,8 +176,9 @@ class IndexFlatIP:
         return {n: getattr(s, n) for n, _ in s._fields_}
 
 
-def merge_topk_host(Ds, Is, k: int, n_threads: int = 0):
-    """Host k-way merge of per-shard (D, I) numpy arrays [nq, k] -> (D, I) [nq, k]."""
+def merge_topk_host(Ds, Is, k: int, n_threads: int = 0, out=None):
+    """Host k-way merge of per-shard (D, I) numpy arrays [nq, k] -> (D, I) [nq, k].  out: optional (D_out, I_out) arrays to
+    write into (reused buffers: a fresh 6 MB result costs more in first-touch page faults than the merge itself)."""
     lib = _lib.load()
     n = len(Ds)
     if n == 0 or n != len(Is):
@@ -188,8 +189,14 @@ def merge_topk_host(Ds, Is, k: int, n_threads: int = 0):
     for d, i in zip(Ds, Is):
         if d.shape != (nq, k) or i.shape != (nq, k):
             raise ValueError(f"every shard must be [{nq}, {k}]")
-    Do = np.empty((nq, k), dtype=np.float32)
-    Io = np.empty((nq, k), dtype=np.int64)
+    if out is not None:
+        Do, Io = out
+        if Do.shape != (nq, k) or Io.shape != (nq, k) or Do.dtype != np.float32 or Io.dtype != np.int64 \
+                or not Do.flags.c_contiguous or not Io.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous (float32 [nq, k], int64 [nq, k])")
+    else:
+        Do = np.empty((nq, k), dtype=np.float32)
+        Io = np.empty((nq, k), dtype=np.int64)
     dp = (C.c_void_p * n)(*[d.ctypes.data for d in Ds])
     ip = (C.c_void_p * n)(*[i.ctypes.data for i in Is])
     _lib.check(lib.ance_merge_topk_host(dp, ip, n, nq, k, Do.ctypes.data, Io.ctypes.data, n_threads))
