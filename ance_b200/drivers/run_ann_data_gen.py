@@ -326,22 +326,28 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
     side = torch.cuda.Stream(device=dev) if cuda else None
     stage = _staging(QB, k, W > 1, cuda)
     pool = _merge_pool()
-    own_I: List[np.ndarray] = []
-    own_q: List[np.ndarray] = []
+    # the queries this rank owns: `part` of every block (all of it when W == 1); their merged labels are written straight
+    # into one result array (no per-block temporaries)
+    owned = [(b0 + rank * part, max(0, min(part, min(QB, nq - b0) - rank * part))) if W > 1 else (b0, min(QB, nq - b0))
+             for b0 in range(0, nq, QB)]
+    starts = np.concatenate([[0], np.cumsum([n for _, n in owned])]).astype(np.int64)
+    I_own = np.empty((int(starts[-1]), k), dtype=np.int64)
+    q_own = (np.concatenate([np.arange(q0, q0 + n, dtype=np.int64) for q0, n in owned]) if owned
+             else np.empty((0,), dtype=np.int64))
 
-    def finish(st: _Staging, ev, n_valid: int, q0: int):
+    def finish(st: _Staging, ev, bi: int):
         if ev is not None:
             ev.synchronize()
+        n_valid = owned[bi][1]
+        dst = I_own[starts[bi]:starts[bi] + n_valid]
         if W == 1:
-            own_I.append(st.I[:n_valid].numpy().copy())
-        else:
+            dst[:] = st.I[:n_valid].numpy()
+        elif n_valid:
             Dv, Iv = st.D.numpy().reshape(W, part, k), st.I.numpy().reshape(W, part, k)
-            if st.merged is None or st.merged[0].shape[0] < n_valid:
-                st.merged = (np.empty((part, k), dtype=np.float32), np.empty((part, k), dtype=np.int64))
-            _, Im = merge_topk_host([Dv[s, :n_valid] for s in range(W)], [Iv[s, :n_valid] for s in range(W)], k,
-                                    merge_threads, out=(st.merged[0][:n_valid], st.merged[1][:n_valid]))
-            own_I.append(Im.copy())
-        own_q.append(np.arange(q0, q0 + n_valid, dtype=np.int64))
+            if st.merged is None:
+                st.merged = np.empty((part, k), dtype=np.float32)       # merged scores: scratch, only the labels are kept
+            merge_topk_host([Dv[s, :n_valid] for s in range(W)], [Iv[s, :n_valid] for s in range(W)], k, merge_threads,
+                            out=(st.merged[:n_valid], dst))
 
     for bi, b0 in enumerate(range(0, nq, QB)):
         nb = min(QB, nq - b0)
@@ -358,10 +364,8 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
             Dr, Ir = torch.empty_like(D), torch.empty_like(I)
             dist.all_to_all_single(Dr, D)          # Dr[s*part:(s+1)*part] = shard s's lists for my part of the block
             dist.all_to_all_single(Ir, I)
-            n_valid = max(0, min(part, nb - rank * part))
-            q0 = b0 + rank * part
         else:
-            Dr, Ir, n_valid, q0 = None, I, nb, b0
+            Dr, Ir = None, I
         ev = None
         if cuda:
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -377,12 +381,10 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
             if Dr is not None:
                 st.D.copy_(Dr)
             st.I[:Ir.shape[0]].copy_(Ir)
-        st.job = pool.submit(finish, st, ev, n_valid, q0)
+        st.job = pool.submit(finish, st, ev, bi)
     for st in stage:
         if st.job is not None:
             st.job.result()
-    I_own = np.concatenate(own_I) if own_I else np.empty((0, k), dtype=np.int64)
-    q_own = np.concatenate(own_q) if own_q else np.empty((0,), dtype=np.int64)
     if not gather_to_rank0:
         return I_own, q_own
     if W == 1:
