@@ -277,19 +277,33 @@ class _Staging:
         self.job = None
 
 
-_STAGING_CACHE: Dict[tuple, list] = {}     # (rows, k, with_scores, pinned) -> two buffers, kept across calls
+_STAGING_CACHE: Dict[tuple, list] = {}     # (rows, k, with_scores, pinned) -> sets of two buffers, kept across calls
 _MERGE_POOL = None
 
 
-def _staging(rows: int, k: int, with_scores: bool, pin: bool):
+class _StagingSet:
+    def __init__(self, rows: int, k: int, with_scores: bool, pin: bool):
+        self.slots = [_Staging(rows, k, with_scores, pin) for _ in range(2)]
+        self.busy = False
+
+
+def _staging(rows: int, k: int, with_scores: bool, pin: bool) -> "_StagingSet":
+    """A free set of two staging buffers of this shape (a search in flight owns its set until `finish()`)."""
     key = (rows, k, with_scores, pin)
-    if key not in _STAGING_CACHE:
-        if len(_STAGING_CACHE) > 8:
-            _STAGING_CACHE.clear()
-        _STAGING_CACHE[key] = [_Staging(rows, k, with_scores, pin) for _ in range(2)]
-    for st in _STAGING_CACHE[key]:
+    sets = _STAGING_CACHE.setdefault(key, [])
+    if len(_STAGING_CACHE) > 8:
+        for kk in [kk for kk in _STAGING_CACHE if kk != key and not any(x.busy for x in _STAGING_CACHE[kk])]:
+            del _STAGING_CACHE[kk]
+    for ss in sets:
+        if not ss.busy:
+            break
+    else:
+        ss = _StagingSet(rows, k, with_scores, pin)
+        sets.append(ss)
+    ss.busy = True
+    for st in ss.slots:
         st.job = None
-    return _STAGING_CACHE[key]
+    return ss
 
 
 def _merge_pool():
@@ -300,21 +314,52 @@ def _merge_pool():
     return _MERGE_POOL
 
 
-def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch.Tensor, k: int,
-                   merge_threads: int = 0, query_block: int = QUERY_BLOCK, gather_to_rank0: bool = True,
-                   row_offset: Optional[int] = None) -> Optional[np.ndarray]:
-    """Every rank searches its own rows for ALL queries; the per-shard top-k lists of a query are merged on the rank
-    that OWNS the query, so the merge (and its device->host copy) is spread over all ranks instead of serialised on
-    rank 0, and it overlaps the search of the next query block:
+class PendingSearch:
+    """A sharded search whose device work, all-to-alls, device->host copies and merges have been issued; `finish()` waits
+    for the merges and does the final gather.  Between the two the caller may enqueue more device work (bench.py encodes the
+    next slice while the previous slice's lists are merged on the host).  Every rank must call `finish()` once, in the same
+    order relative to its other collectives."""
 
-        for each block of `query_block` queries                        (device work on the current stream)
-            D, I = local_search(block)                                   per-shard top-k, labels already global
-            all_to_all(D), all_to_all(I)                                 rank r receives the W lists of ITS 1/W of the block
-            async D2H into pinned staging  ->  host k-way merge (C++, worker thread)      || next block's search
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
 
-    Returns I [nq, k] (global rows, merged order) on rank 0 and None elsewhere; with gather_to_rank0=False every rank
-    gets the merged lists of the queries it owns as (I_own [n_own, k], own_query_numbers).  row_offset: global number
-    of this rank's first row (= rows of the ranks before it); computed with one small all-gather when not given."""
+    def finish(self, gather_to_rank0: bool = True):
+        for st in self.sset.slots:
+            if st.job is not None:
+                st.job.result()
+                st.job = None
+        self.sset.busy = False
+        W, rank, nq, QB, part, k, dev, I_own = self.W, self.rank, self.nq, self.QB, self.part, self.k, self.dev, self.I_own
+        if not gather_to_rank0:
+            return I_own, self.q_own
+        if W == 1:
+            return I_own
+        # final assembly on rank 0 (post-processing and the output files are rank 0's, run_ann_data_gen.py:265-336):
+        # nq x k labels in total, 1/W of what a gather of the per-shard lists would move
+        n_blocks = (nq + QB - 1) // QB
+        mine = torch.full((n_blocks * part, k), -1, dtype=torch.int64)
+        mine[:I_own.shape[0]] = torch.from_numpy(I_own)
+        mine = mine.to(dev)
+        if rank == 0:
+            parts = [torch.empty_like(mine) for _ in range(W)]
+            dist.gather(mine, parts, dst=0)
+            out = np.empty((nq, k), dtype=np.int64)
+            for r in range(W):
+                pr = parts[r].cpu().numpy()
+                row = 0
+                for b0 in range(0, nq, QB):
+                    nv = max(0, min(part, min(QB, nq - b0) - r * part))
+                    out[b0 + r * part:b0 + r * part + nv] = pr[row:row + nv]
+                    row += nv
+            return out
+        dist.gather(mine, None, dst=0)
+        return None
+
+
+def sharded_search_start(local_search: Callable, n_local_rows: int, queries_all: torch.Tensor, k: int,
+                         merge_threads: int = 0, query_block: int = QUERY_BLOCK, row_offset: Optional[int] = None
+                         ) -> PendingSearch:
+    """Issue a sharded search (see `sharded_search`) and return without waiting for the host merges."""
     from ..search import merge_topk_host
     W, rank = _world()
     dev = queries_all.device
@@ -324,7 +369,8 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
     QB = max(W, (max(1, min(query_block, nq)) + W - 1) // W * W)      # a multiple of W: equal all-to-all splits
     part = QB // W
     side = torch.cuda.Stream(device=dev) if cuda else None
-    stage = _staging(QB, k, W > 1, cuda)
+    sset = _staging(QB, k, W > 1, cuda)
+    stage = sset.slots
     pool = _merge_pool()
     # the queries this rank owns: `part` of every block (all of it when W == 1); their merged labels are written straight
     # into one result array (no per-block temporaries)
@@ -335,7 +381,7 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
     q_own = (np.concatenate([np.arange(q0, q0 + n, dtype=np.int64) for q0, n in owned]) if owned
              else np.empty((0,), dtype=np.int64))
 
-    def finish(st: _Staging, ev, bi: int):
+    def finish_block(st: _Staging, ev, bi: int):
         if ev is not None:
             ev.synchronize()
         n_valid = owned[bi][1]
@@ -381,34 +427,27 @@ def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch
             if Dr is not None:
                 st.D.copy_(Dr)
             st.I[:Ir.shape[0]].copy_(Ir)
-        st.job = pool.submit(finish, st, ev, bi)
-    for st in stage:
-        if st.job is not None:
-            st.job.result()
-    if not gather_to_rank0:
-        return I_own, q_own
-    if W == 1:
-        return I_own
-    # final assembly on rank 0 (post-processing and the output files are rank 0's, run_ann_data_gen.py:265-336):
-    # nq x k labels in total, 1/W of what a gather of the per-shard lists would move
-    n_blocks = (nq + QB - 1) // QB
-    mine = torch.full((n_blocks * part, k), -1, dtype=torch.int64)
-    mine[:I_own.shape[0]] = torch.from_numpy(I_own)
-    mine = mine.to(dev)
-    if rank == 0:
-        parts = [torch.empty_like(mine) for _ in range(W)]
-        dist.gather(mine, parts, dst=0)
-        out = np.empty((nq, k), dtype=np.int64)
-        for r in range(W):
-            pr = parts[r].cpu().numpy()
-            row = 0
-            for b0 in range(0, nq, QB):
-                nv = max(0, min(part, min(QB, nq - b0) - r * part))
-                out[b0 + r * part:b0 + r * part + nv] = pr[row:row + nv]
-                row += nv
-        return out
-    dist.gather(mine, None, dst=0)
-    return None
+        st.job = pool.submit(finish_block, st, ev, bi)
+    return PendingSearch(sset=sset, W=W, rank=rank, nq=nq, QB=QB, part=part, k=k, dev=dev, I_own=I_own, q_own=q_own)
+
+
+def sharded_search(local_search: Callable, n_local_rows: int, queries_all: torch.Tensor, k: int,
+                   merge_threads: int = 0, query_block: int = QUERY_BLOCK, gather_to_rank0: bool = True,
+                   row_offset: Optional[int] = None) -> Optional[np.ndarray]:
+    """Every rank searches its own rows for ALL queries; the per-shard top-k lists of a query are merged on the rank
+    that OWNS the query, so the merge (and its device->host copy) is spread over all ranks instead of serialised on
+    rank 0, and it overlaps the search of the next query block:
+
+        for each block of `query_block` queries                        (device work on the current stream)
+            D, I = local_search(block)                                   per-shard top-k, labels already global
+            all_to_all(D), all_to_all(I)                                 rank r receives the W lists of ITS 1/W of the block
+            async D2H into pinned staging  ->  host k-way merge (C++, worker thread)      || next block's search
+
+    Returns I [nq, k] (global rows, merged order) on rank 0 and None elsewhere; with gather_to_rank0=False every rank
+    gets the merged lists of the queries it owns as (I_own [n_own, k], own_query_numbers).  row_offset: global number
+    of this rank's first row (= rows of the ranks before it); computed with one small all-gather when not given."""
+    return sharded_search_start(local_search, n_local_rows, queries_all, k, merge_threads, query_block,
+                                row_offset).finish(gather_to_rank0)
 
 
 # =============================================================================================

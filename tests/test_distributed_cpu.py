@@ -54,11 +54,21 @@ def _worker(rank, world, port, n_p, n_q, k, tmpdir):
         counts = [None] * world
         dist.all_gather_object(counts, own_q.tolist())
         assert sorted(sum(counts, [])) == list(range(n_q))   # ... and every query is owned exactly once
+        # two searches in flight (bench.py at N > 1: the merge of slice i runs while slice i + 1 is encoded and searched):
+        # each owns its staging set; finishing in issue order gives the synchronous results
+        pa = drv.sharded_search_start(local_search, p_loc.shape[0], q_all, k, query_block=5)
+        pb = drv.sharded_search_start(local_search, p_loc.shape[0], q_all.flip(0).contiguous(), k, query_block=5)
+        assert pa.sset is not pb.sset
+        Ia, Ifl = pa.finish(), pb.finish()
+        pc = drv.sharded_search_start(local_search, p_loc.shape[0], q_all, k, query_block=5)   # the sets are free again
+        assert pc.sset in (pa.sset, pb.sset)
+        Ic = pc.finish()
         if rank == 0:
             assert (I == Ig).all() and (Ib == Ig).all()
+            assert (Ia == Ig).all() and (Ic == Ig).all() and (Ifl == Ig[::-1]).all()
             np.save(os.path.join(tmpdir, "I.npy"), I)
         else:
-            assert I is None and Ib is None
+            assert I is None and Ib is None and Ia is None and Ifl is None and Ic is None
         # the reference's StreamingDataset stride under an initialised process group
         lens = np.ones(n_q, dtype=np.int32)
         base = os.path.join(tmpdir, f"cache{rank}")
