@@ -367,3 +367,35 @@ def test_array_negatives_and_native_writer_equal_the_python_path(tmp_path):
             assert n1 == n2 == nq and open(a, "rb").read() == open(b, "rb").read()
     finally:
         postprocess._FAST_CHUNK = old_chunk
+
+
+def test_synthetic_data_dir_is_in_the_reference_formats(tmp_path):
+    """ance_b200.synthetic (bench / full-refresh inputs): token caches readable through the EmbeddingCache contract, one
+    positive per query in the qrels, and the multi-writer form (every rank of a job writes its share of the chunks into the
+    pre-sized file) byte-identical to the single writer."""
+    import filecmp
+    from ance_b200 import synthetic
+    from ance_b200.data import EmbeddingCache, StridedBatchReader
+    from ance_b200.drivers.run_ann_data_gen import load_positive_ids
+    d = tmp_path / "data"
+    synthetic.write_marco_like_dir(str(d), 700, 60, 11, L_p=32, L_q=16, seed=3, vocab=500)
+    with EmbeddingCache(str(d / "passages")) as c:
+        assert len(c) == 700 and c.embedding_size == 32
+        n, ids = c[699]
+        assert 8 <= n <= 32 and ids[0] == 0 and ids[n - 1] == 2 and (ids[n:] == 1).all() and ids[:n].max() < 500
+        with pytest.raises(IndexError):
+            c[700]
+    seen = [int(i) for _, _, idx in StridedBatchReader(EmbeddingCache(str(d / "train-query")), 7, 1, 3, pin=False) for i in idx]
+    assert seen == list(range(1, 60, 3))
+    train_pos, dev_pos = load_positive_ids(argparse.Namespace(data_dir=str(d)))
+    assert sorted(train_pos) == list(range(60)) and sorted(dev_pos) == list(range(11))
+    assert all(0 <= p < 700 for p in train_pos.values())
+    # the same cache written by three "ranks" sharing the chunks
+    synthetic.write_token_cache(str(tmp_path / "one"), 1000, 16, 9, 3, 4, 5, chunk=128)
+    synthetic.presize_token_cache(str(tmp_path / "many"), 1000, 16)
+    for part in range(3):
+        synthetic.write_token_cache(str(tmp_path / "many"), 1000, 16, 9, 3, 4, 5, chunk=128, part=part, n_parts=3)
+    assert filecmp.cmp(tmp_path / "one", tmp_path / "many", shallow=False)
+    full = tmp_path / "full"
+    synthetic.write_token_cache(str(full), 50, 16, 9, 3, 4, 5, full_length=True)
+    assert (EmbeddingCache(str(full)).memmap()["len"] == 16).all()
