@@ -671,11 +671,6 @@ __global__ void gather_rows16_kernel(const uint16_t* __restrict__ src, const int
   for (int i = threadIdx.x; i < d / 8; i += blockDim.x) o[i] = s[i];
 }
 
-__global__ void fill_i32(int* p, int n, int v) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
-
 }  // namespace
 
 // ================================================================================================
