@@ -292,3 +292,44 @@ class StridedBatchReader:
             if self.pin:
                 ids, lens = ids.pin_memory(), lens.pin_memory()
             yield ids, lens, idx_t
+
+
+class AnnDataWatcher:
+    """The trainer's in-process hot swap of ANN training data (drivers/run_ann.py:182-228), as one object.
+
+    The reference's training loop polls `get_latest_ann_data(args.ann_dir)` every `logging_steps`, and when the refresher has
+    published a new `ann_ndcg_N` it re-reads `ann_training_data_N`, truncates it to a multiple of the world size
+    (`aligned_size`, run_ann.py:193-195), rebuilds its streaming dataset and restarts the iterator.  `poll()` does exactly
+    that and returns None when nothing new is there, else a `Swap` with the reference's bookkeeping values (`ann_no`,
+    `dev_ndcg`, `checkpoint`, `checkpoint_no`, number of lines) and a fresh `TripletBatchReader` over the new lines for this
+    rank.  It only ever sees complete files: the refresher publishes `ann_training_data_N` first and `ann_ndcg_N` last, both
+    through an atomic rename (ance_b200/postprocess.py)."""
+
+    class Swap:
+        def __init__(self, ann_no, ann_path, ndcg_json, lines, reader):
+            self.ann_no, self.ann_path, self.lines, self.reader = ann_no, ann_path, lines, reader
+            self.dev_ndcg = ndcg_json.get("ndcg")
+            self.checkpoint = ndcg_json.get("checkpoint")
+            import re
+            nums = re.findall(r"\d+", self.checkpoint or "")
+            self.checkpoint_no = int(nums[-1]) if nums else 0      # utils/util.py:224-226
+
+    def __init__(self, ann_dir: str, query_cache: "EmbeddingCache", passage_cache: "EmbeddingCache", batch_size: int,
+                 max_query_length: int, max_seq_length: int, rank: int = 0, world_size: int = 1, pin: bool = True):
+        self.ann_dir, self.qc, self.pc = ann_dir, query_cache, passage_cache
+        self.batch_size, self.lq, self.lp = batch_size, max_query_length, max_seq_length
+        self.rank, self.world, self.pin = rank, world_size, pin
+        self.last_ann_no = -1
+
+    def poll(self):
+        from .drivers.run_ann_data_gen import get_latest_ann_data
+        ann_no, ann_path, ndcg_json = get_latest_ann_data(self.ann_dir)
+        if ann_path is None or ann_no == self.last_ann_no:
+            return None
+        with open(ann_path, "r") as f:
+            lines = f.readlines()
+        lines = lines[:(len(lines) // self.world) * self.world]         # aligned_size
+        reader = TripletBatchReader(lines, self.qc, self.pc, self.batch_size, self.lq, self.lp, rank=self.rank,
+                                    world_size=self.world, pin=self.pin)
+        self.last_ann_no = ann_no
+        return AnnDataWatcher.Swap(ann_no, ann_path, ndcg_json, lines, reader)

@@ -121,3 +121,34 @@ def test_gpu_forward_loss(losses, golden_dir):
                                            refresh_oracle.maxp_logits(q[:2], d[::-1], first[::-1]))
     assert float(lossm) == pytest.approx(want, abs=1e-3)
     assert float(lossm) == pytest.approx(losses["multi_chunk_loss"], abs=3.0)
+
+
+def test_ann_data_watcher_hot_swaps_like_the_training_loop(rec, tmp_path):
+    """drivers/run_ann.py:182-228 as an object: nothing until the refresher publishes ann_ndcg_N, then the new lines
+    (truncated to a multiple of the world size), the bookkeeping values the loop logs, and a reader over this rank's
+    triplets; a leftover staged file or a data file without its json is never picked up."""
+    from ance_b200 import postprocess
+    from ance_b200.data import AnnDataWatcher
+    qc, pc = _caches(rec, tmp_path)
+    ann = tmp_path / "ann"
+    ann.mkdir()
+    lines = rec["lines"]
+    with qc, pc:
+        w = AnnDataWatcher(str(ann), qc, pc, 4, rec["Lq"], rec["Lp"], rank=1, world_size=2, pin=False)
+        assert w.poll() is None
+        (ann / "ann_training_data_0").write_text("".join(lines))          # data first ...
+        open(postprocess.staging_path(str(ann / "ann_ndcg_0")), "w").write("{partial")
+        assert w.poll() is None                                            # ... not visible before the json lands
+        postprocess.write_ndcg(str(ann / "ann_ndcg_0"), 0.25, "out/checkpoint-3000/")
+        s = w.poll()
+        assert s is not None and (s.ann_no, s.dev_ndcg, s.checkpoint_no) == (0, 0.25, 3000)
+        assert len(s.lines) == (len(lines) // 2) * 2 and s.ann_path.endswith("ann_training_data_0")
+        want = refresh_oracle.training_triplets(s.lines[1::2], rec["qlens"], np.asarray(rec["qids"]), rec["plens"],
+                                                np.asarray(rec["pids"]), rec["Lq"], rec["Lp"])
+        got = sum(q.shape[0] for q, *_ in s.reader)
+        assert got == len(want)
+        assert w.poll() is None                                            # same refresh: no swap
+        (ann / "ann_training_data_1").write_text("".join(lines[:5]))
+        postprocess.write_ndcg(str(ann / "ann_ndcg_1"), 0.5, "out/checkpoint-6000/")
+        s2 = w.poll()
+        assert (s2.ann_no, s2.checkpoint_no, len(s2.lines)) == (1, 6000, 4) and w.poll() is None
