@@ -530,7 +530,7 @@ def run_b200(args, wl):
     out = {
         "metric": wl["metric"], "value": units / ms * 1e3, "unit": wl["unit"], "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.encoder_operand + " operands / fp32 accumulate",
+        "vs_baseline": None, "dtype": args.encoder_operand,   # 16-bit tensor-core operands and storage, fp32 accumulation / statistics
         "data": "synthetic", "config": workload_config(args, wl, world),
         "stages": {
             "passages_encoded_per_s": (pb + qb * L_q / L_p) * args.steps / enc_ms * 1e3 * world,
