@@ -207,7 +207,7 @@ class B200Backend:
                     self.model.encode_lens(ids_d, lens_d, out=out)
                     i = idx.numpy()
                 if index is not None:
-                    index.add(out)     # in place: quantise to the 16-bit operands, no copy
+                    index.add(out)     # in place: the slice already IS index storage (no copy; operands are built by prepare())
                 ids_out.append(i)
                 pos += out.shape[0]
         if hasattr(self.model, "check_inputs"):
