@@ -63,7 +63,11 @@ def _worker(rank, world, port, n_p, n_q, k, tmpdir):
         pc = drv.sharded_search_start(local_search, p_loc.shape[0], q_all, k, query_block=5)   # the sets are free again
         assert pc.sset in (pa.sset, pb.sset)
         Ic = pc.finish()
+        # edges: fewer queries than ranks, and none at all
+        I1 = drv.sharded_search(local_search, p_loc.shape[0], q_all[:1].contiguous(), k)
+        I0 = drv.sharded_search(local_search, p_loc.shape[0], q_all[:0].contiguous(), k)
         if rank == 0:
+            assert (I1 == Ig[:1]).all() and I0.shape == (0, k)
             assert (I == Ig).all() and (Ib == Ig).all()
             assert (Ia == Ig).all() and (Ic == Ig).all() and (Ifl == Ig[::-1]).all()
             np.save(os.path.join(tmpdir, "I.npy"), I)
